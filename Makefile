@@ -1,0 +1,40 @@
+# Builds everything in-tree (built artefacts are git-ignored but travel to the GPU box):
+#   skid_b200/libskidgpu.so   the CUDA hot path behind the C-ABI of include/skidgpu.h (sm_100a only)
+#   host/skid                 flag-compatible C driver (SKID's main.c surface) linked against it
+#   oracle/liboracle.so       CPU restatement of the reference algorithm (TEST INFRASTRUCTURE)
+#   oracle/_ref/*             the unmodified reference, when /root/reference is present
+NVCC ?= /usr/local/cuda/bin/nvcc
+CC ?= gcc
+NVFLAGS = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function
+CUSRC = $(wildcard skid_b200/csrc/*.cu)
+CUOBJ = $(CUSRC:.cu=.o)
+CUHDR = $(wildcard skid_b200/csrc/*.cuh) include/skidgpu.h
+
+all: lib host oracle
+
+lib: skid_b200/libskidgpu.so
+
+skid_b200/csrc/%.o: skid_b200/csrc/%.cu $(CUHDR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+skid_b200/libskidgpu.so: $(CUOBJ)
+	$(NVCC) -shared -o $@ $(CUOBJ) -gencode arch=compute_100a,code=sm_100a
+
+host: host/skid
+
+host/skid: host/skid_main.c host/tipsy_io.c host/outputs.c host/cosmo.c host/skid_host.h include/skidgpu.h skid_b200/libskidgpu.so
+	$(CC) -O2 -Wall -Iinclude -o $@ host/skid_main.c host/tipsy_io.c host/outputs.c host/cosmo.c \
+		-Lskid_b200 -lskidgpu -Wl,-rpath,'$$ORIGIN/../skid_b200' -lm
+
+oracle: oracle/liboracle.so ref
+
+oracle/liboracle.so: oracle/skid_oracle.c oracle/skid_oracle.h
+	$(CC) -O2 -fPIC -shared -Wall -ffp-contract=off -o $@ oracle/skid_oracle.c -lm
+
+ref:
+	./oracle/build_ref.sh
+
+clean:
+	rm -f skid_b200/csrc/*.o skid_b200/libskidgpu.so host/skid oracle/liboracle.so
+
+.PHONY: all lib host oracle ref clean

@@ -1,0 +1,387 @@
+// extern "C" entry points of libskidgpu (include/skidgpu.h).  No exceptions cross the ABI.
+#include "ctx.cuh"
+#include <algorithm>
+
+#define API_BEGIN(ctx)                                                                                 \
+	if (!(ctx)) return SKIDGPU_ERR;                                                                \
+	try {                                                                                          \
+		CK(cudaSetDevice((ctx)->device));
+#define API_END(ctx)                                                                                   \
+	}                                                                                              \
+	catch (const std::exception &e)                                                                \
+	{                                                                                              \
+		(ctx)->err = e.what();                                                                 \
+		return SKIDGPU_ERR;                                                                    \
+	}                                                                                              \
+	return SKIDGPU_OK;
+
+static std::string g_create_err;
+
+extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPeriod[3], const float fCenter[3],
+                              int bPeriodic, int bDiag)
+{
+	if (!pctx) return SKIDGPU_ERR;
+	*pctx = nullptr;
+	skidgpu_ctx *c = nullptr;
+	try {
+		int nDev = 0;
+		cudaError_t e = cudaGetDeviceCount(&nDev);
+		if (e != cudaSuccess || nDev <= 0)
+			throw SkidError(std::string("skidgpu_create: no usable CUDA device (") + cudaGetErrorString(e) +
+			                "); this library has no CPU fallback");
+		if (device < 0 || device >= nDev) throw SkidError("skidgpu_create: bad device ordinal");
+		CK(cudaSetDevice(device));
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, device));
+		if (prop.major < 10)
+			throw SkidError("skidgpu_create: device is not sm_100 (Blackwell); this library is built for sm_100a only");
+		c = new skidgpu_ctx();
+		c->device = device;
+		for (int d = 0; d < 3; ++d) {
+			c->L[d] = fPeriod[d];
+			c->C[d] = fCenter[d];
+		}
+		c->bPeriodic = bPeriodic;
+		c->bDiag = bDiag;
+		CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		CK(cudaEventCreate(&c->ev0));
+		CK(cudaEventCreate(&c->ev1));
+		*pctx = c;
+	} catch (const std::exception &e) {
+		g_create_err = e.what();
+		fprintf(stderr, "%s\n", e.what());
+		delete c;
+		return SKIDGPU_ERR;
+	}
+	return SKIDGPU_OK;
+}
+
+extern "C" void skidgpu_destroy(skidgpu_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	cudaStream_t s = ctx->stream;
+	delete ctx;
+	if (s) cudaStreamDestroy(s);
+}
+
+extern "C" const char *skidgpu_last_error(skidgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int skidgpu_set_shard(skidgpu_ctx *ctx, int rank, int nranks)
+{
+	API_BEGIN(ctx)
+	if (nranks < 1 || rank < 0 || rank >= nranks) throw SkidError("skidgpu_set_shard: bad rank/nranks");
+	ctx->rank = rank;
+	ctx->nranks = nranks;
+	API_END(ctx)
+}
+
+__global__ void __launch_bounds__(256)
+    k_aos_to_soa(int n, const skidgpu_pinit *p, float *x, float *y, float *z, float *vx, float *vy, float *vz,
+                 float *mass, float *soft, float *temp)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	skidgpu_pinit q = p[i];
+	x[i] = q.r[0];
+	y[i] = q.r[1];
+	z[i] = q.r[2];
+	vx[i] = q.v[0];
+	vy[i] = q.v[1];
+	vz[i] = q.v[2];
+	mass[i] = q.fMass;
+	soft[i] = q.fSoft;
+	temp[i] = q.fTemp;
+}
+
+static void set_counts(skidgpu_ctx *c, int n, int nGas, int nDark, int nStar)
+{
+	if (n <= 0 || nGas < 0 || nDark < 0 || nStar < 0 || nGas + nDark + nStar != n)
+		throw SkidError("skidgpu_set_particles: need n = nGas + nDark + nStar > 0");
+	c->n = n;
+	c->nGas = nGas;
+	c->nDark = nDark;
+	c->nStar = nStar;
+	c->inType = (nDark ? SKIDGPU_DARK : 0) | (nGas ? SKIDGPU_GAS : 0) | (nStar ? SKIDGPU_STAR : 0); // kd.c:143-149
+	c->nMove = c->nActive = 0;
+	c->nGroup = 0;
+	c->nEnt = c->nExtra = c->nAct = 0;
+	c->haveCenters = false;
+	c->x.alloc(n);
+	c->y.alloc(n);
+	c->z.alloc(n);
+	c->vx.alloc(n);
+	c->vy.alloc(n);
+	c->vz.alloc(n);
+	c->mass.alloc(n);
+	c->soft.alloc(n);
+	c->temp.alloc(n);
+}
+
+extern "C" int skidgpu_set_particles(skidgpu_ctx *ctx, const skidgpu_pinit *p, int n, int nGas, int nDark, int nStar)
+{
+	API_BEGIN(ctx)
+	if (!p) throw SkidError("skidgpu_set_particles: null particle array");
+	set_counts(ctx, n, nGas, nDark, nStar);
+	for (int i = 0; i < n; i += (n > 4096 ? n / 7 + 1 : 1))
+		if (p[i].iOrder != i) throw SkidError("skidgpu_set_particles: particles must be in file order (iOrder == index)");
+	skidgpu_pinit *d = ctx->aos.alloc(n);
+	CK(cudaMemcpyAsync(d, p, sizeof(skidgpu_pinit) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	SK_LAUNCH(k_aos_to_soa, (unsigned)ceil_div(n, 256), 256, 0, ctx->stream, n, d, ctx->x.p, ctx->y.p, ctx->z.p, ctx->vx.p,
+	          ctx->vy.p, ctx->vz.p, ctx->mass.p, ctx->soft.p, ctx->temp.p);
+	CK(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_set_particles_dev(skidgpu_ctx *ctx, const float *dx, const float *dy, const float *dz,
+                                         const float *dvx, const float *dvy, const float *dvz, const float *dmass,
+                                         const float *dsoft, const float *dtemp, int n, int nGas, int nDark,
+                                         int nStar)
+{
+	API_BEGIN(ctx)
+	set_counts(ctx, n, nGas, nDark, nStar);
+	const float *src[9] = {dx, dy, dz, dvx, dvy, dvz, dmass, dsoft, dtemp};
+	float *dst[9] = {ctx->x.p, ctx->y.p, ctx->z.p, ctx->vx.p, ctx->vy.p, ctx->vz.p, ctx->mass.p, ctx->soft.p, ctx->temp.p};
+	for (int k = 0; k < 9; ++k) {
+		if (!src[k]) throw SkidError("skidgpu_set_particles_dev: null device array");
+		CK(cudaMemcpyAsync(dst[k], src[k], sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+__global__ void __launch_bounds__(256) k_fill(int n, float *a, float v)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) a[i] = v;
+}
+
+extern "C" int skidgpu_set_soft(skidgpu_ctx *ctx, float fEps)
+{
+	API_BEGIN(ctx)
+	if (ctx->n <= 0) throw SkidError("skidgpu_set_soft: no particles set");
+	SK_LAUNCH(k_fill, (unsigned)ceil_div(ctx->n, 256), 256, 0, ctx->stream, ctx->n, ctx->soft.p, fEps);
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_density(skidgpu_ctx *ctx, int nSmooth, int bGasAndDark, int bGasOnly, float *rho_by_iOrder,
+                               float *ball2_by_iOrder, int *nExtraScat)
+{
+	API_BEGIN(ctx)
+	stage_density(*ctx, nSmooth, bGasAndDark, bGasOnly, nExtraScat);
+	if (rho_by_iOrder)
+		CK(cudaMemcpyAsync(rho_by_iOrder, ctx->rho.p, sizeof(float) * (size_t)ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+	if (ball2_by_iOrder)
+		CK(cudaMemcpyAsync(ball2_by_iOrder, ctx->ball2.p, sizeof(float) * (size_t)ctx->n, cudaMemcpyDeviceToHost,
+		                   ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_keep_neighbors(skidgpu_ctx *ctx, int bKeep)
+{
+	API_BEGIN(ctx)
+	ctx->keepNbr = bKeep != 0;
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_get_neighbors(skidgpu_ctx *ctx, int *nbr, float *d2)
+{
+	API_BEGIN(ctx)
+	if (!ctx->keepNbr || !ctx->nbr.p) throw SkidError("skidgpu_get_neighbors: enable skidgpu_keep_neighbors before skidgpu_density");
+	size_t cnt = (size_t)ctx->n * ctx->nSmooth;
+	if (nbr) CK(cudaMemcpyAsync(nbr, ctx->nbr.p, sizeof(int) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+	if (d2) CK(cudaMemcpyAsync(d2, ctx->nbrD2.p, sizeof(float) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_move(skidgpu_ctx *ctx, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
+                            int bForceInitialCut, int bNoPrune, skidgpu_log_cb cb, void *user, int *nMove, int *nIttr)
+{
+	API_BEGIN(ctx)
+	stage_move(*ctx, fDensMin, fTempMax, fMassMax, fCvg, fStep, bForceInitialCut, bNoPrune, cb, user, nMove, nIttr);
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_keep_step0(skidgpu_ctx *ctx, int bKeep)
+{
+	API_BEGIN(ctx)
+	ctx->keepStep0 = bKeep != 0;
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_get_step0(skidgpu_ctx *ctx, int *iOrder, float *a3, unsigned char *scat_alive_by_iOrder)
+{
+	API_BEGIN(ctx)
+	if (!ctx->keepStep0 || !ctx->a0x.p) throw SkidError("skidgpu_get_step0: enable skidgpu_keep_step0 before skidgpu_move");
+	const int m = ctx->nMove;
+	std::vector<float> hx(m), hy(m), hz(m);
+	cudaStream_t s = ctx->stream;
+	if (iOrder) CK(cudaMemcpyAsync(iOrder, ctx->mOrd.p, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(hx.data(), ctx->a0x.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(hy.data(), ctx->a0y.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(hz.data(), ctx->a0z.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+	if (scat_alive_by_iOrder && ctx->aliveByOrd.p)
+		CK(cudaMemcpyAsync(scat_alive_by_iOrder, ctx->aliveByOrd.p, ctx->n, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (a3)
+		for (int i = 0; i < m; ++i) {
+			a3[3 * i] = hx[i];
+			a3[3 * i + 1] = hy[i];
+			a3[3 * i + 2] = hz[i];
+		}
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_fof(skidgpu_ctx *ctx, float fTau, int *nGroup)
+{
+	API_BEGIN(ctx)
+	stage_fof(*ctx, fTau, nGroup);
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_microstep(skidgpu_ctx *ctx, int nSteps, float fStep, skidgpu_log_cb cb, void *user)
+{
+	API_BEGIN(ctx)
+	stage_microstep(*ctx, nSteps, fStep, cb, user);
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_get_moved(skidgpu_ctx *ctx, int *iOrder, float *r3)
+{
+	API_BEGIN(ctx)
+	const int m = ctx->nMove;
+	if (m > 0) {
+		std::vector<float> hx(m), hy(m), hz(m);
+		std::vector<int> ord(m);
+		cudaStream_t s = ctx->stream;
+		CK(cudaMemcpyAsync(ord.data(), ctx->mOrd.p, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+		CK(cudaMemcpyAsync(hx.data(), ctx->mx.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+		CK(cudaMemcpyAsync(hy.data(), ctx->my.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+		CK(cudaMemcpyAsync(hz.data(), ctx->mz.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		// movers live in Morton order on the device; kdOutVector wants iOrder order (kd.c:1561)
+		std::vector<int> idx(m);
+		for (int i = 0; i < m; ++i) idx[i] = i;
+		std::sort(idx.begin(), idx.end(), [&](int a, int b) { return ord[a] < ord[b]; });
+		for (int i = 0; i < m; ++i) {
+			int j = idx[i];
+			if (iOrder) iOrder[i] = ord[j];
+			if (r3) {
+				r3[3 * i] = hx[j];
+				r3[3 * i + 1] = hy[j];
+				r3[3 * i + 2] = hz[j];
+			}
+		}
+	}
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_moved_dev(skidgpu_ctx *ctx, float **dxyz, int *nMove, int *lo, int *hi)
+{
+	API_BEGIN(ctx)
+	const int m = ctx->nMove;
+	float *b = ctx->mxyz.alloc((size_t)3 * (m > 0 ? m : 1));
+	cudaStream_t s = ctx->stream;
+	if (m > 0) {
+		CK(cudaMemcpyAsync(b, ctx->mx.p, sizeof(float) * m, cudaMemcpyDeviceToDevice, s));
+		CK(cudaMemcpyAsync(b + m, ctx->my.p, sizeof(float) * m, cudaMemcpyDeviceToDevice, s));
+		CK(cudaMemcpyAsync(b + 2 * (size_t)m, ctx->mz.p, sizeof(float) * m, cudaMemcpyDeviceToDevice, s));
+	}
+	CK(cudaStreamSynchronize(s));
+	if (dxyz) *dxyz = b;
+	if (nMove) *nMove = m;
+	if (lo) *lo = ctx->shardLo;
+	if (hi) *hi = ctx->shardHi;
+	API_END(ctx)
+}
+
+static void fetch_catalogue(skidgpu_ctx *ctx, int *piGroup, skidgpu_pgroup *g)
+{
+	cudaStream_t s = ctx->stream;
+	if (piGroup) CK(cudaMemcpyAsync(piGroup, ctx->gid.p, sizeof(int) * (size_t)ctx->n, cudaMemcpyDeviceToHost, s));
+	if (g) CK(cudaMemcpyAsync(g, ctx->gCat.p, sizeof(skidgpu_pgroup) * (size_t)ctx->nGroup, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+}
+
+extern "C" int skidgpu_centers(skidgpu_ctx *ctx, int *piGroup_by_iOrder, skidgpu_pgroup *g)
+{
+	API_BEGIN(ctx)
+	stage_centers(*ctx);
+	fetch_catalogue(ctx, piGroup_by_iOrder, g);
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_set_groups(skidgpu_ctx *ctx, const int *piGroup_by_iOrder, int nGroup,
+                                  const skidgpu_pgroup *centres)
+{
+	API_BEGIN(ctx)
+	if (!piGroup_by_iOrder) throw SkidError("skidgpu_set_groups: null group array");
+	stage_set_groups(*ctx, piGroup_by_iOrder, nGroup, centres);
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_unbind(skidgpu_ctx *ctx, float fG, float z, double fCosmo, int iSoftType, float fScoop,
+                              int bNoUnbind, int nMaxMembers, int nMinMembers, int *piGroup_by_iOrder,
+                              skidgpu_pgroup *g, int *nGroup, int *nUnbound, int *nGroupBefore)
+{
+	API_BEGIN(ctx)
+	stage_unbind(*ctx, fG, z, fCosmo, iSoftType, fScoop, bNoUnbind, nMaxMembers, nMinMembers, nUnbound, nGroupBefore);
+	if (nGroup) *nGroup = ctx->nGroup;
+	fetch_catalogue(ctx, piGroup_by_iOrder, g);
+	API_END(ctx)
+}
+
+extern "C" double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage)
+{
+	if (!ctx || stage < 0 || stage > 5) return -1.0;
+	return ctx->stage_ms[stage];
+}
+
+extern "C" long long skidgpu_counter(skidgpu_ctx *ctx, int which)
+{
+	if (!ctx) return -1;
+	switch (which) {
+	case 0: return g_skid_launches;
+	case 1: return ctx->moverSteps;
+	case 2: return ctx->nQueries;
+	case 3: return ctx->nPairs;
+	}
+	return -1;
+}
+
+// ---- test hooks for the hand-written primitives (host arrays in, host arrays out)
+extern "C" int skidgpu_debug_sort(skidgpu_ctx *ctx, unsigned long long *keys, unsigned int *vals, long long n, int bits)
+{
+	API_BEGIN(ctx)
+	DevBuf<uint64_t> k;
+	DevBuf<uint32_t> v;
+	k.alloc(n > 0 ? n : 1);
+	v.alloc(n > 0 ? n : 1);
+	cudaStream_t s = ctx->stream;
+	CK(cudaMemcpyAsync(k.p, keys, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, s));
+	CK(cudaMemcpyAsync(v.p, vals, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+	radix_sort_pairs(k.p, v.p, (size_t)n, bits, ctx->ws, s);
+	CK(cudaMemcpyAsync(keys, k.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(vals, v.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_debug_scan(skidgpu_ctx *ctx, const unsigned int *in, unsigned int *out, long long n)
+{
+	API_BEGIN(ctx)
+	DevBuf<uint32_t> a, b;
+	a.alloc(n > 0 ? n : 1);
+	b.alloc(n + 1);
+	cudaStream_t s = ctx->stream;
+	CK(cudaMemcpyAsync(a.p, in, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+	exclusive_scan_u32(a.p, b.p, (size_t)n, ctx->ws, s);
+	CK(cudaMemcpyAsync(out, b.p, sizeof(uint32_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	API_END(ctx)
+}

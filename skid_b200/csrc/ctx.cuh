@@ -1,0 +1,103 @@
+// Context of the skidgpu library: device-resident state shared by the stage files.
+#pragma once
+#include "common.cuh"
+#include "../../include/skidgpu.h"
+
+struct skidgpu_ctx {
+	int device = 0;
+	cudaStream_t stream = 0;
+	std::string err;
+	float L[3], C[3];
+	int bPeriodic = 0, bDiag = 0;
+	int rank = 0, nranks = 1;
+
+	// ---- particles, SoA by iOrder (file order: gas, dark, star; kd.c:113-119)
+	int n = 0, nGas = 0, nDark = 0, nStar = 0, inType = 0;
+	DevBuf<float> x, y, z, vx, vy, vz, mass, soft, temp;
+	DevBuf<float> rho, ball2; // by iOrder; 0 for non scatter-active
+	DevBuf<skidgpu_pinit> aos; // staging for the AoS upload
+	Workspace ws;
+
+	// ---- scatter-active set + kNN tree (stage 1/2)
+	int nAct = 0, nSmooth = 0, bGasAndDark = 0, bGasOnly = 0;
+	DevBuf<uint32_t> flags, scan;
+	DevBuf<uint32_t> actIdx;  // compacted file indices of scatter-active particles
+	DevBuf<float> ax_, ay_, az_; // gathered positions of the active set (tree input)
+	BoxTree treeA;
+	DevBuf<float4> posA;   // sorted (x,y,z,mass)
+	DevBuf<int> iordA;     // sorted position -> file index
+	DevBuf<float> ball2A;  // sorted
+	DevBuf<double> rho64A; // sorted, f64 accumulators
+	DevBuf<float> rhoA;    // sorted, final f32 density
+	bool keepNbr = false;
+	DevBuf<int> nbr;
+	DevBuf<float> nbrD2;
+
+	// ---- scatterer entities = active originals + periodic replicas (smooth1.c:278-332)
+	int nEnt = 0, nExtra = 0;
+	DevBuf<float> ex, ey, ez, eInfl, eRhoSorted;
+	DevBuf<float4> entPosU;  // unsorted (x,y,z,ball2)
+	DevBuf<float2> entNRU;   // unsorted (fNorm, rho)
+	DevBuf<uint32_t> entSrcU; // unsorted: sorted-A index | 0x80000000 for a replica
+	DevBuf<float4> entPos;   // sorted (x,y,z,ball2)
+	DevBuf<float2> entNR;    // sorted (fNorm, rhoEff): rhoEff = 0 once cut at step 0
+	DevBuf<uint32_t> entSrc;
+	DevBuf<uint8_t> entTouched;
+	BoxTree treeE;
+
+	// ---- movers (kd.c:630-666), Morton order of their initial positions
+	int nMove = 0, nActive = 0, bNoPrune = 0;
+	long long moverSteps = 0;
+	DevBuf<float> mx, my, mz, rox, roy, roz;
+	DevBuf<int> mOrd; // mover id -> iOrder
+	DevBuf<uint32_t> actList, actList2;
+	DevBuf<float> tmpx, tmpy, tmpz;
+	BoxTree treeM;
+	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step
+	DevBuf<uint32_t> dCount;
+	bool keepStep0 = false;
+	DevBuf<float> a0x, a0y, a0z;
+	DevBuf<uint8_t> aliveByOrd;
+	int shardLo = 0, shardHi = 0;
+	DevBuf<float> mxyz; // contiguous x|y|z copy for the multi-GPU exchange
+
+	// ---- groups
+	int nGroup = 0; // groups + 1 (kd->nGroup)
+	DevBuf<int> gid;    // by iOrder
+	DevBuf<int> repOrd; // per group: iOrder of its reference member (rel)
+	DevBuf<int> gN;
+	DevBuf<double> gAcc; // per group accumulators
+	DevBuf<skidgpu_pgroup> gCat;
+	std::vector<skidgpu_pgroup> hCat;
+	bool haveCenters = false;
+
+	// ---- timing / counters
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	double stage_ms[6] = {0, 0, 0, 0, 0, 0};
+	long long nQueries = 0, nPairs = 0;
+};
+
+// stage entry points (each in its own .cu)
+void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, int *nExtraScat);
+void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
+                int bForceInitialCut, int bNoPrune, skidgpu_log_cb cb, void *user, int *nMove, int *nIttr);
+void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb, void *user);
+void stage_fof(skidgpu_ctx &c, float fTau, int *nGroup);
+void stage_centers(skidgpu_ctx &c);
+void stage_set_groups(skidgpu_ctx &c, const int *piGroup, int nGroup, const skidgpu_pgroup *centres);
+void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmo, int iSoftType, float fScoop,
+                  int bNoUnbind, int nMaxMembers, int nMinMembers, int *nUnbound, int *nGroupBefore);
+
+struct StageTimer {
+	skidgpu_ctx &c;
+	int stage;
+	StageTimer(skidgpu_ctx &c_, int st) : c(c_), stage(st) { CK(cudaEventRecord(c.ev0, c.stream)); }
+	void stop()
+	{
+		CK(cudaEventRecord(c.ev1, c.stream));
+		CK(cudaEventSynchronize(c.ev1));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+		c.stage_ms[stage] = ms;
+	}
+};

@@ -1,0 +1,459 @@
+// Stage 3: density-gradient "flow" of the moving particles until they converge.
+//
+// Replaces kdInitMove/CutCriterion (kd.c:555-666), kdBuildMoveTree (kd.c:463-552),
+// smBallGather (smooth1.c:338-384), smAccDensity + ScatterCut (smooth1.c:387-518),
+// kdMoveParticles (kd.c:702-732), kdPruneInactive (kd.c:735-793), kdReactivateMove (kd.c:796)
+// and the loops of main.c:394-419,431-438.
+//
+// The reference rebuilds a kd-tree over the MOVERS every step and lets every fixed scatterer
+// scatter grad(W) onto the movers inside its ball.  Here the form is inverted: the scatterers
+// (originals + explicit periodic replicas) never move, so ONE static tree with ball-inflated boxes
+// is built once (density.cu) and every mover gathers from the scatterers whose ball contains it.
+// Same set of (scatterer, mover) interactions, same float32 hit test, no per-step tree build.
+// Scatterer pruning state of the reference is reproduced with two numbers per step:
+// T (entities with rho < T are gone) and the per-entity "cut at step 0" flag (rhoEff = 0).
+#include "ctx.cuh"
+#include <utility>
+
+#define T_NONE 0x7f800000u // +inf bits: "no entity was hit this step"
+
+// CutCriterion (kd.c:555-597)
+__global__ void __launch_bounds__(256)
+    k_mover_flags(int n, int nGas, int nDark, int inType, int bGasAndDark, int bGasOnly, const float *rho,
+                  const float *temp, const float *mass, float fDensMin, float fTempMax, float fMassMax,
+                  uint32_t *flags)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int t = i < nGas ? SKIDGPU_GAS : (i < nGas + nDark ? SKIDGPU_DARK : SKIDGPU_STAR);
+	int f = 0;
+	float d = rho[i];
+	if (!(mass[i] > fMassMax)) {
+		switch (inType) {
+		case SKIDGPU_DARK: f = d >= fDensMin; break;
+		case SKIDGPU_GAS:
+		case SKIDGPU_DARK | SKIDGPU_GAS:
+			if (bGasAndDark && t == SKIDGPU_DARK && d >= fDensMin) f = 1;
+			if (t == SKIDGPU_GAS && d >= fDensMin && temp[i] <= fTempMax) f = 1;
+			break;
+		case SKIDGPU_STAR:
+		case SKIDGPU_DARK | SKIDGPU_STAR: f = (t == SKIDGPU_STAR); break;
+		case SKIDGPU_GAS | SKIDGPU_STAR:
+		case SKIDGPU_DARK | SKIDGPU_GAS | SKIDGPU_STAR:
+			if (bGasAndDark && t == SKIDGPU_DARK && d >= fDensMin) f = 1;
+			if (t == SKIDGPU_GAS) {
+				if (d >= fDensMin && temp[i] <= fTempMax) f = 1;
+			} else if (t == SKIDGPU_STAR && !bGasOnly) f = 1;
+			break;
+		}
+	}
+	flags[i] = (uint32_t)f;
+}
+
+__global__ void __launch_bounds__(256) k_compact_idx2(int n, const uint32_t *flags, const uint32_t *scan,
+                                                      uint32_t *out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && flags[i]) out[scan[i]] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_gather3b(int m, const uint32_t *idx, const float *x, const float *y,
+                                                  const float *z, float *ox, float *oy, float *oz)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	uint32_t j = idx[i];
+	ox[i] = x[j];
+	oy[i] = y[j];
+	oz[i] = z[j];
+}
+
+// movers in Morton order: r = rOld = initial position, mOrd = iOrder (kd.c:653-662)
+__global__ void __launch_bounds__(256)
+    k_init_movers(int m, const uint32_t *perm, const uint32_t *fileIdx, const float *x, const float *y,
+                  const float *z, float *mx, float *my, float *mz, float *rox, float *roy, float *roz, int *mOrd)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	uint32_t j = fileIdx[perm[i]];
+	float px = x[j], py = y[j], pz = z[j];
+	mx[i] = px;
+	my[i] = py;
+	mz[i] = pz;
+	rox[i] = px;
+	roy[i] = py;
+	roz[i] = pz;
+	mOrd[i] = (int)j;
+}
+
+__global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < cnt) out[i] = (uint32_t)(lo + i);
+}
+
+struct StepArgs {
+	TreeView tv;
+	const float4 *entPos; // (x,y,z,fBall2)
+	const float2 *entNR;  // (fNorm, rhoEff)
+	uint8_t *touched;     // nullable: set for entities with >= 1 hit (step 0, initial cut)
+	float *mx, *my, *mz;
+	const uint32_t *act;
+	int nActive;
+	int nEnt;
+	uint32_t *dT; // [0] threshold T (float bits), [1] running min of rho over hit entities (float bits)
+	float fStep;
+	float L[3];
+	double wrapLo[3], wrapHi[3];
+	float *a0x, *a0y, *a0z; // nullable: keep accelerations
+};
+
+constexpr int STEP_WARPS = 8;
+
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+	if (wi >= a.nActive) return;
+	const uint32_t id = a.act[wi];
+	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+	const float T = __uint_as_float(a.dT[0]);
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	float rmin = 3.0e38f;
+
+	int lev = a.tv.top - 1;
+	uint32_t node = 0;
+	uint32_t mymask = 0;
+#define STEP_TEST_CHILDREN()                                                                           \
+	{                                                                                              \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		float4 lo = bx[0], hi = bx[1];                                                         \
+		bool in_ = x >= lo.x && x <= hi.x && y >= lo.y && y <= hi.y && z >= lo.z && z <= hi.z && \
+		           lo.w >= T;                                                                  \
+		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+	STEP_TEST_CHILDREN();
+	while (true) {
+		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
+		if (m == 0) {
+			++lev;
+			if (lev >= a.tv.top) break;
+			node >>= 5;
+			continue;
+		}
+		int c = __ffs(m) - 1;
+		m &= m - 1;
+		if (lane == lev) mymask = m;
+		uint32_t child = node * 32 + c;
+		if (lev > 0) {
+			--lev;
+			node = child;
+			STEP_TEST_CHILDREN();
+			continue;
+		}
+		int e = (int)child * 32 + lane;
+		if (e < a.nEnt) {
+			float4 p = a.entPos[e];
+			// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
+			float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+			float d2 = dist2_rn(dx, dy, dz);
+			if (d2 < p.w) {
+				float2 nr = a.entNR[e];
+				if (nr.y >= T) {
+					// smAccDensity (smooth1.c:447-459)
+					float ih2 = __fdiv_rn(4.0f, p.w);
+					float r2 = __fmul_rn(d2, ih2);
+					float rs = __fsqrt_rn(r2);
+					if (r2 < 1.0f) rs = (float)(-3.0 + 2.25 * (double)rs);
+					else rs = (float)(-3.0 / (double)rs + 3.0 - 0.75 * (double)rs);
+					rs = __fmul_rn(rs, nr.x);
+					ax = __fadd_rn(ax, __fmul_rn(dx, rs));
+					ay = __fadd_rn(ay, __fmul_rn(dy, rs));
+					az = __fadd_rn(az, __fmul_rn(dz, rs));
+					rmin = fminf(rmin, nr.y);
+					if (a.touched) a.touched[e] = 1;
+				}
+			}
+		}
+	}
+#undef STEP_TEST_CHILDREN
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		ax += __shfl_xor_sync(SK_FULL, ax, o);
+		ay += __shfl_xor_sync(SK_FULL, ay, o);
+		az += __shfl_xor_sync(SK_FULL, az, o);
+		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
+	}
+	if (lane == 0) {
+		if (rmin < 3.0e38f) atomicMin(&a.dT[1], __float_as_uint(rmin)); // smooth1.c:460-461 (rho > 0)
+		if (a.a0x) {
+			a.a0x[id] = ax;
+			a.a0y[id] = ay;
+			a.a0z[id] = az;
+		}
+		// kdMoveParticles (kd.c:711-729)
+		float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+		float ai = (float)sqrt((double)s2);
+		if (ai > 0.0f) ai = (float)((double)a.fStep / sqrt((double)s2));
+		else ai = 0.0f;
+		float r[3] = {__fsub_rn(x, __fmul_rn(ai, ax)), __fsub_rn(y, __fmul_rn(ai, ay)),
+		              __fsub_rn(z, __fmul_rn(ai, az))};
+#pragma unroll
+		for (int j = 0; j < 3; ++j) {
+			if ((double)r[j] > a.wrapHi[j]) r[j] = __fsub_rn(r[j], a.L[j]);
+			if ((double)r[j] <= a.wrapLo[j]) r[j] = __fadd_rn(r[j], a.L[j]);
+		}
+		a.mx[id] = r[0];
+		a.my[id] = r[1];
+		a.mz[id] = r[2];
+	}
+}
+
+// After a step: adopt the new threshold (ScatterCut, smooth1.c:509-513).  If nothing was hit the
+// reference's fScatDens stays 0.0 and nothing is cut.
+__global__ void k_update_T(uint32_t *dT, int bNoPrune)
+{
+	uint32_t nx = dT[1];
+	if (!bNoPrune && nx != T_NONE) dT[0] = nx;
+	dT[1] = T_NONE;
+}
+
+// Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
+__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float2 *entNR)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < nEnt && !touched[e]) entNR[e].y = 0.0f;
+}
+
+// nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517)
+__global__ void __launch_bounds__(256) k_count_scatter(int nEnt, const float2 *entNR, const uint32_t *dT,
+                                                       uint32_t *out)
+{
+	float T = __uint_as_float(dT[0]);
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	bool alive = e < nEnt && entNR[e].y >= T;
+	uint32_t b = __ballot_sync(SK_FULL, alive);
+	if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (uint32_t)__popc(b));
+}
+
+__global__ void __launch_bounds__(256)
+    k_alive_by_order(int nEnt, const float2 *entNR, const uint32_t *entSrc, const int *iordA, const uint32_t *dT,
+                     uint8_t *alive)
+{
+	float T = __uint_as_float(dT[0]);
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nEnt) return;
+	uint32_t s = entSrc[e];
+	if (s & 0x80000000u) return;
+	alive[iordA[s]] = entNR[e].y >= T ? 1 : 0;
+}
+
+// kdPruneInactive (kd.c:735-793): a mover stays active iff it moved >= fCvg (min image) since the
+// last check.  flags -> scan -> stable compaction of the active list.
+__global__ void __launch_bounds__(256)
+    k_prune_flags(int nActive, const uint32_t *act, const float *mx, const float *my, const float *mz,
+                  const float *rox, const float *roy, const float *roz, float hx, float hy, float hz, float fCvg2,
+                  uint32_t *flags)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nActive) return;
+	uint32_t id = act[i];
+	float dx = __fsub_rn(mx[id], rox[id]);
+	float dy = __fsub_rn(my[id], roy[id]);
+	float dz = __fsub_rn(mz[id], roz[id]);
+	float tx = __fmul_rn(2.0f, hx), ty = __fmul_rn(2.0f, hy), tz = __fmul_rn(2.0f, hz);
+	if (dx > hx) dx = __fsub_rn(dx, tx);
+	if (dx <= -hx) dx = __fadd_rn(dx, tx);
+	if (dy > hy) dy = __fsub_rn(dy, ty);
+	if (dy <= -hy) dy = __fadd_rn(dy, ty);
+	if (dz > hz) dz = __fsub_rn(dz, tz);
+	if (dz <= -hz) dz = __fadd_rn(dz, tz);
+	float dr2 = dist2_rn(dx, dy, dz);
+	flags[i] = dr2 >= fCvg2 ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+    k_prune_compact(int nActive, const uint32_t *act, const uint32_t *flags, const uint32_t *scan,
+                    const float *mx, const float *my, const float *mz, float *rox, float *roy, float *roz,
+                    uint32_t *actOut)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nActive || !flags[i]) return;
+	uint32_t id = act[i];
+	actOut[scan[i]] = id;
+	rox[id] = mx[id];
+	roy[id] = my[id];
+	roz[id] = mz[id];
+}
+
+static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
+{
+	sa.tv = tree_view(c.treeE);
+	sa.entPos = c.entPos.p;
+	sa.entNR = c.entNR.p;
+	sa.touched = nullptr;
+	sa.mx = c.mx.p;
+	sa.my = c.my.p;
+	sa.mz = c.mz.p;
+	sa.act = c.actList.p;
+	sa.nActive = c.nActive;
+	sa.nEnt = c.nEnt;
+	sa.dT = c.dT.p;
+	sa.fStep = fStep;
+	for (int d = 0; d < 3; ++d) {
+		sa.L[d] = c.L[d];
+		sa.wrapHi[d] = (double)c.C[d] + 0.5 * (double)c.L[d]; // kd.c:724
+		sa.wrapLo[d] = (double)c.C[d] - 0.5 * (double)c.L[d]; // kd.c:726
+	}
+	sa.a0x = sa.a0y = sa.a0z = nullptr;
+}
+
+static int count_scatterers(skidgpu_ctx &c)
+{
+	cudaStream_t s = c.stream;
+	uint32_t *cnt = c.dCount.alloc(4);
+	CK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t), s));
+	if (c.nEnt > 0)
+		SK_LAUNCH(k_count_scatter, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entNR.p, c.dT.p, cnt);
+	uint32_t h = 0;
+	CK(cudaMemcpyAsync(&h, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	return (int)h;
+}
+
+static void one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
+{
+	if (c.nActive > 0 && c.nEnt > 0) {
+		sa.act = c.actList.p;
+		sa.nActive = c.nActive;
+		SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
+		c.moverSteps += c.nActive;
+	}
+	SK_LAUNCH(k_update_T, 1, 1, 0, c.stream, c.dT.p, bNoPrune);
+}
+
+void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
+                int bForceInitialCut, int bNoPrune, skidgpu_log_cb cb, void *user, int *nMoveOut, int *nIttrOut)
+{
+	cudaStream_t s = c.stream;
+	const int n = c.n;
+	if (n <= 0) throw SkidError("skidgpu_move: no particles set");
+	if (!c.rho.p) throw SkidError("skidgpu_move: skidgpu_density has not run");
+	StageTimer tm(c, 1);
+	c.bNoPrune = bNoPrune;
+
+	// ---- kdInitMove
+	uint32_t *flags = c.flags.alloc(n);
+	uint32_t *scan = c.scan.alloc((size_t)n + 64);
+	SK_LAUNCH(k_mover_flags, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.nGas, c.nDark, c.inType, c.bGasAndDark,
+	          c.bGasOnly, c.rho.p, c.temp.p, c.mass.p, fDensMin, fTempMax, fMassMax, flags);
+	exclusive_scan_u32(flags, scan, n, c.ws, s);
+	uint32_t nm = 0;
+	CK(cudaMemcpyAsync(&nm, scan + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	c.nMove = (int)nm;
+	c.haveCenters = false;
+	const int m = c.nMove;
+	uint32_t *dT = c.dT.alloc(4);
+	uint32_t initT[2] = {0u, T_NONE};
+	CK(cudaMemcpyAsync(dT, initT, sizeof initT, cudaMemcpyHostToDevice, s));
+	c.shardLo = (int)((long long)m * c.rank / c.nranks);
+	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
+	c.nActive = c.shardHi - c.shardLo;
+	if (m > 0) {
+		uint32_t *fileIdx = c.actList2.alloc(m);
+		SK_LAUNCH(k_compact_idx2, (unsigned)ceil_div(n, 256), 256, 0, s, n, flags, scan, fileIdx);
+		float *gx = c.tmpx.alloc(m), *gy = c.tmpy.alloc(m), *gz = c.tmpz.alloc(m);
+		SK_LAUNCH(k_gather3b, (unsigned)ceil_div(m, 256), 256, 0, s, m, fileIdx, c.x.p, c.y.p, c.z.p, gx, gy, gz);
+		tree_sort_points(c.treeM, gx, gy, gz, m, c.ws, s);
+		c.mx.alloc(m);
+		c.my.alloc(m);
+		c.mz.alloc(m);
+		c.rox.alloc(m);
+		c.roy.alloc(m);
+		c.roz.alloc(m);
+		c.mOrd.alloc(m);
+		SK_LAUNCH(k_init_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeM.perm.p, fileIdx, c.x.p, c.y.p,
+		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p);
+		c.actList.alloc(m);
+		c.actList2.alloc(m); // fileIdx no longer needed after k_init_movers (same stream)
+		if (c.nActive > 0)
+			SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.shardLo, c.nActive, c.actList.p);
+	}
+	if (nMoveOut) *nMoveOut = m;
+
+	// ---- step 0 (main.c:396-404)
+	const int bInitial = ((c.inType == SKIDGPU_DARK) || bForceInitialCut) && !bNoPrune;
+	StepArgs sa;
+	fill_step_args(c, sa, fStep);
+	if (c.keepStep0 && m > 0) {
+		sa.a0x = c.a0x.alloc(m);
+		sa.a0y = c.a0y.alloc(m);
+		sa.a0z = c.a0z.alloc(m);
+		CK(cudaMemsetAsync(sa.a0x, 0, sizeof(float) * m, s));
+		CK(cudaMemsetAsync(sa.a0y, 0, sizeof(float) * m, s));
+		CK(cudaMemsetAsync(sa.a0z, 0, sizeof(float) * m, s));
+	}
+	if (bInitial && c.nEnt > 0) {
+		CK(cudaMemsetAsync(c.entTouched.p, 0, c.nEnt, s));
+		sa.touched = c.entTouched.p;
+	}
+	int nActiveLog = c.nActive;
+	one_step(c, sa, bNoPrune);
+	if (bInitial && c.nEnt > 0 && c.nranks == 1)
+		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p);
+	sa.touched = nullptr;
+	sa.a0x = sa.a0y = sa.a0z = nullptr;
+	if (c.keepStep0 && c.nEnt > 0) {
+		CK(cudaMemsetAsync(c.aliveByOrd.alloc(n), 0, n, s));
+		SK_LAUNCH(k_alive_by_order, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entNR.p, c.entSrc.p,
+		          c.iordA.p, c.dT.p, c.aliveByOrd.p);
+	}
+	int nScat = count_scatterers(c);
+	if (cb) cb(user, 0, 0, nActiveLog, nScat);
+
+	// ---- main flow loop (main.c:408-419)
+	const float hx = (float)(0.5 * (double)c.L[0]), hy = (float)(0.5 * (double)c.L[1]),
+	            hz = (float)(0.5 * (double)c.L[2]);
+	const float fCvg2 = fCvg * fCvg;
+	int nIttr = 1;
+	while (c.nActive) {
+		for (int i = 0; i < 5; ++i) one_step(c, sa, bNoPrune);
+		// kdPruneInactive
+		uint32_t *pf = c.flags.alloc(c.nActive);
+		uint32_t *ps = c.scan.alloc((size_t)c.nActive + 64);
+		SK_LAUNCH(k_prune_flags, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
+		          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, hx, hy, hz, fCvg2, pf);
+		exclusive_scan_u32(pf, ps, c.nActive, c.ws, s);
+		SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, ps,
+		          c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p);
+		uint32_t na = 0;
+		CK(cudaMemcpyAsync(&na, ps + c.nActive, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		nScat = count_scatterers(c); // synchronises
+		c.nActive = (int)na;
+		std::swap(c.actList.p, c.actList2.p);
+		std::swap(c.actList.cap, c.actList2.cap);
+		if (cb) cb(user, 0, nIttr, c.nActive, nScat);
+		++nIttr;
+	}
+	if (nIttrOut) *nIttrOut = nIttr;
+	tm.stop();
+}
+
+void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb, void *user)
+{
+	cudaStream_t s = c.stream;
+	StageTimer tm(c, 3);
+	// kdReactivateMove (kd.c:796-799)
+	c.nActive = c.shardHi - c.shardLo;
+	if (c.nActive > 0)
+		SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.shardLo, c.nActive, c.actList.p);
+	StepArgs sa;
+	fill_step_args(c, sa, fStep);
+	for (int i = 0; i < nSteps; ++i) {
+		one_step(c, sa, c.bNoPrune); // smAccDensity keeps cutting scatterers during the micro steps
+		if (cb) cb(user, 1, i + 1, c.nActive, count_scatterers(c));
+	}
+	tm.stop();
+}

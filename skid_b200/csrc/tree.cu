@@ -1,0 +1,206 @@
+// Stage 1: spatial index build.  Replaces kdBuildTree (kd.c:371-460; kdSelectInit 225-253,
+// UpPassInit 307-336, Combine 287-304).  The reference builds a balanced median-split binary
+// kd-tree with 16-particle buckets; tree shape does not affect any result (only tie order), so
+// the GPU index is designed for warp-wide traversal instead: points are sorted by 63-bit Morton
+// key, cut into buckets of 32 consecutive points (one coalesced 512 B float4 load per bucket),
+// and every internal node has 32 children so a warp tests all child boxes of a node at once.
+#include "common.cuh"
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v)
+{
+	uint64_t x = v & 0x1fffffu;
+	x = (x | (x << 32)) & 0x1f00000000ffffull;
+	x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+	x = (x | (x << 8)) & 0x100f00f00f00f00full;
+	x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+	x = (x | (x << 2)) & 0x1249249249249249ull;
+	return x;
+}
+
+__global__ void k_bbox_init(float *bbox)
+{
+	if (threadIdx.x < 3) ((unsigned int *)bbox)[threadIdx.x] = 0xffffffffu;      // flipped +max
+	else if (threadIdx.x < 6) ((unsigned int *)bbox)[threadIdx.x] = 0u;         // flipped -max
+}
+
+__global__ void __launch_bounds__(256) k_bbox(const float *x, const float *y, const float *z, int n,
+                                              float *bbox)
+{
+	float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		float p[3] = {x[i], y[i], z[i]};
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			lo[d] = fminf(lo[d], p[d]);
+			hi[d] = fmaxf(hi[d], p[d]);
+		}
+	}
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			lo[d] = fminf(lo[d], __shfl_xor_sync(SK_FULL, lo[d], o));
+			hi[d] = fmaxf(hi[d], __shfl_xor_sync(SK_FULL, hi[d], o));
+		}
+	}
+	if ((threadIdx.x & 31) == 0) {
+		unsigned int *b = (unsigned int *)bbox;
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			atomicMin(&b[d], float_flip(lo[d]));
+			atomicMax(&b[3 + d], float_flip(hi[d]));
+		}
+	}
+}
+
+__global__ void k_bbox_finish(float *bbox)
+{
+	if (threadIdx.x < 6) bbox[threadIdx.x] = float_unflip(((unsigned int *)bbox)[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float *x, const float *y, const float *z, int n,
+                                                const float *bbox, uint64_t *keys, uint32_t *perm)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float p[3] = {x[i], y[i], z[i]};
+	uint32_t q[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		double ext = (double)bbox[3 + d] - (double)bbox[d];
+		double t = ext > 0.0 ? ((double)p[d] - (double)bbox[d]) / ext : 0.0;
+		long long v = (long long)(t * 2097152.0);
+		if (v < 0) v = 0;
+		if (v > 2097151) v = 2097151;
+		q[d] = (uint32_t)v;
+	}
+	keys[i] = (spread21(q[2]) << 2) | (spread21(q[1]) << 1) | spread21(q[0]);
+	perm[i] = (uint32_t)i;
+}
+
+// bounding box of n points into t.bbox (device: lo[3], hi[3])
+void tree_bbox_only(BoxTree &t, const float *x, const float *y, const float *z, int n, cudaStream_t s)
+{
+	float *bbox = t.bbox.alloc(8);
+	SK_LAUNCH(k_bbox_init, 1, 32, 0, s, bbox);
+	int nb = (int)ceil_div(n > 0 ? n : 1, 256);
+	if (nb > 1184) nb = 1184;
+	SK_LAUNCH(k_bbox, nb, 256, 0, s, x, y, z, n, bbox);
+	SK_LAUNCH(k_bbox_finish, 1, 32, 0, s, bbox);
+}
+
+void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z, int n, Workspace &ws,
+                      cudaStream_t s)
+{
+	t.n = n;
+	float *bbox = t.bbox.alloc(8);
+	uint64_t *keys = t.keys.alloc(n > 0 ? n : 1);
+	uint32_t *perm = t.perm.alloc(n > 0 ? n : 1);
+	if (n == 0) return;
+	tree_bbox_only(t, x, y, z, n, s);
+	SK_LAUNCH(k_morton, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, keys, perm);
+	radix_sort_pairs(keys, perm, n, 63, ws, s);
+}
+
+// One warp per bucket of 32 sorted points.
+__global__ void __launch_bounds__(256) k_leaf_boxes(const float4 *pos4, const float *infl, const float *aux,
+                                                    int n, float4 *box, int nBoxPadded)
+{
+	int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (b >= nBoxPadded) return;
+	int lane = threadIdx.x & 31;
+	int i = b * 32 + lane;
+	float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+	float a = -3.0e38f;
+	if (i < n) {
+		float4 p = pos4[i];
+		float h = infl ? infl[i] : 0.0f;
+		lo[0] = __fadd_rd(p.x, -h);
+		lo[1] = __fadd_rd(p.y, -h);
+		lo[2] = __fadd_rd(p.z, -h);
+		hi[0] = __fadd_ru(p.x, h);
+		hi[1] = __fadd_ru(p.y, h);
+		hi[2] = __fadd_ru(p.z, h);
+		if (aux) a = aux[i];
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			lo[d] = fminf(lo[d], __shfl_xor_sync(SK_FULL, lo[d], o));
+			hi[d] = fmaxf(hi[d], __shfl_xor_sync(SK_FULL, hi[d], o));
+		}
+		a = fmaxf(a, __shfl_xor_sync(SK_FULL, a, o));
+	}
+	if (lane == 0) {
+		box[2 * b] = make_float4(lo[0], lo[1], lo[2], a);
+		box[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+	}
+}
+
+// One warp per parent: union of up to 32 child boxes.
+__global__ void __launch_bounds__(256) k_upper_boxes(const float4 *child, int nChild, float4 *box,
+                                                     int nBoxPadded)
+{
+	int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (b >= nBoxPadded) return;
+	int lane = threadIdx.x & 31;
+	int c = b * 32 + lane;
+	float4 lo = make_float4(3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f);
+	float4 hi = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.0f);
+	if (c < nChild) {
+		lo = child[2 * c];
+		hi = child[2 * c + 1];
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		lo.x = fminf(lo.x, __shfl_xor_sync(SK_FULL, lo.x, o));
+		lo.y = fminf(lo.y, __shfl_xor_sync(SK_FULL, lo.y, o));
+		lo.z = fminf(lo.z, __shfl_xor_sync(SK_FULL, lo.z, o));
+		lo.w = fmaxf(lo.w, __shfl_xor_sync(SK_FULL, lo.w, o));
+		hi.x = fmaxf(hi.x, __shfl_xor_sync(SK_FULL, hi.x, o));
+		hi.y = fmaxf(hi.y, __shfl_xor_sync(SK_FULL, hi.y, o));
+		hi.z = fmaxf(hi.z, __shfl_xor_sync(SK_FULL, hi.z, o));
+	}
+	if (lane == 0) {
+		box[2 * b] = lo;
+		box[2 * b + 1] = hi;
+	}
+}
+
+void tree_build_boxes(BoxTree &t, const float4 *pos4, const float *infl, const float *aux, int n,
+                      cudaStream_t s)
+{
+	t.n = n;
+	// level sizes
+	int cnt[SK_MAXLEV], pad[SK_MAXLEV];
+	int top = 0;
+	int c = (int)ceil_div(n > 0 ? n : 1, 32);
+	while (true) {
+		if (top >= SK_MAXLEV) throw SkidError("tree_build_boxes: too many levels");
+		cnt[top] = c;
+		pad[top] = (int)ceil_div(c, 32) * 32;
+		++top;
+		if (c <= 32) break;
+		c = (int)ceil_div(c, 32);
+	}
+	size_t total = 0;
+	for (int l = 0; l < top; ++l) total += 2 * (size_t)pad[l];
+	float4 *base = t.store.alloc(total);
+	size_t off = 0;
+	for (int l = 0; l < SK_MAXLEV; ++l) {
+		t.box[l] = nullptr;
+		t.cnt[l] = 0;
+	}
+	for (int l = 0; l < top; ++l) {
+		t.box[l] = base + off;
+		t.cnt[l] = cnt[l];
+		off += 2 * (size_t)pad[l];
+	}
+	t.top = top;
+	SK_LAUNCH(k_leaf_boxes, (unsigned)ceil_div((size_t)pad[0] * 32, 256), 256, 0, s, pos4, infl, aux, n,
+	          t.box[0], pad[0]);
+	for (int l = 1; l < top; ++l)
+		SK_LAUNCH(k_upper_boxes, (unsigned)ceil_div((size_t)pad[l] * 32, 256), 256, 0, s, t.box[l - 1],
+		          cnt[l - 1], t.box[l], pad[l]);
+}
