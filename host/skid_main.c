@@ -1,0 +1,284 @@
+/*
+ * skid (B200): drop-in driver with SKID v1.4.1's command line, stdin TIPSY input and
+ * .grp/.gtp/.den/.ray/.stat outputs (reference main.c:17-499), calling the GPU stages through
+ * include/skidgpu.h.  Flags are the reference's (main.c:140-335) plus two extensions:
+ *   -nsp       never prune scatterers (README:29-32 describes it; main.c never implemented it)
+ *   -gpu <n>   CUDA device ordinal (default 0)
+ */
+#include <float.h>
+#include <limits.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#include "skid_host.h"
+
+#define PRUNE_STEPS 5
+#define MICRO_STEP 0.1
+
+static void usage(void)
+{
+	fputs("USAGE:\n"
+	      "skid -tau <fLinkLength> [OPTIONAL ARGUMENTS]\n"
+	      "	 reads TIPSY BINARY input file from stdin\n"
+	      "     [-std]\n"
+	      "COSMOLOGY and UNITS arguments:\n"
+	      "     [-z <fRedShift>] [-O <fOmega>]\n"
+	      "     [-G <fGravConst>] [-H <fHubble>]\n"
+	      "     [-Lambda <fLambda>] [-Q <fQuintessense]\n"
+	      "GROUP FINDING arguments (see man page!):\n"
+	      "     [-s <nSmooth>] [-d <fMinDensity>] [-t <fMaxTemp>]\n"
+	      "     [-cvg <fConvergeRadius>] [-scoop <fScoopRadius>]\n"
+	      "     [-m <nMinMembers>] [-nu] [-gd] [-unbind <GroupName>[.grp]]\n"
+	      "     [-M <fMaxMass>] [-fic] [-go] [-maxgroup nMaxMembers] [-nsp]\n"
+	      "GRAVITATIONAL SOFTENING arguments:\n"
+	      "     [-spline] [-plummer] [-e <fSoft>]\n"
+	      "PERIODIC BOX specification:\n"
+	      "     [-p <xyzPeriod>]\n"
+	      "     [-c <xyzCenter>]\n"
+	      "     [-cx <xCenter>] [-cy <yCenter>] [-cz <zCenter>]\n"
+	      "OUTPUT arguments:\n"
+	      "     [-o <Output Name>] [-ray] [-den] [-stats] [-diag] [-gpu <device>]\n"
+	      "\nSee man page skid(1).\n",
+	      stderr);
+	exit(1);
+}
+
+typedef struct {
+	int bTau, bCvg, bScoop, bEps, bPeriodic, bStandard;
+	int nSmooth, nMembers, nMaxMembers, iSoftType;
+	int bNoUnbind, bGasAndDark, bGasOnly, bUnbindOnly, bForceInitialCut, bNoPrune;
+	int bOutRay, bOutDens, bOutStats, bOutDiag, iDevice;
+	float fTau, z, Omega0, Lambda, fQuintess, G, H0;
+	float fDensMin, fTempMax, fMassMax, fCvg, fScoop, fEps;
+	float fPeriod[3], fCenter[3];
+	char achGroup[256], achName[256];
+} options;
+
+enum { A_FLAG, A_FLOAT, A_INT, A_STR };
+typedef struct {
+	const char *name;
+	int kind;
+	size_t off;     /* value field */
+	size_t off_set; /* "was given" flag field or 0 */
+	int flagval;
+} optdef;
+#define OFF(f) offsetof(options, f)
+
+static const optdef g_opts[] = {
+    {"-tau", A_FLOAT, OFF(fTau), OFF(bTau), 0},
+    {"-z", A_FLOAT, OFF(z), 0, 0},
+    {"-O", A_FLOAT, OFF(Omega0), 0, 0},
+    {"-Lambda", A_FLOAT, OFF(Lambda), 0, 0},
+    {"-Q", A_FLOAT, OFF(fQuintess), 0, 0},
+    {"-G", A_FLOAT, OFF(G), 0, 0},
+    {"-H", A_FLOAT, OFF(H0), 0, 0},
+    {"-s", A_INT, OFF(nSmooth), 0, 0},
+    {"-d", A_FLOAT, OFF(fDensMin), 0, 0},
+    {"-t", A_FLOAT, OFF(fTempMax), 0, 0},
+    {"-M", A_FLOAT, OFF(fMassMax), 0, 0},
+    {"-fic", A_FLAG, OFF(bForceInitialCut), 0, 1},
+    {"-cvg", A_FLOAT, OFF(fCvg), OFF(bCvg), 0},
+    {"-scoop", A_FLOAT, OFF(fScoop), OFF(bScoop), 0},
+    {"-m", A_INT, OFF(nMembers), 0, 0},
+    {"-maxgroup", A_INT, OFF(nMaxMembers), 0, 0},
+    {"-nu", A_FLAG, OFF(bNoUnbind), 0, 1},
+    {"-gd", A_FLAG, OFF(bGasAndDark), 0, 1},
+    {"-go", A_FLAG, OFF(bGasOnly), 0, 1},
+    {"-nsp", A_FLAG, OFF(bNoPrune), 0, 1},
+    {"-unbind", A_STR, OFF(achGroup), OFF(bUnbindOnly), 0},
+    {"-spline", A_FLAG, OFF(iSoftType), 0, SKIDGPU_SPLINE},
+    {"-plummer", A_FLAG, OFF(iSoftType), 0, SKIDGPU_PLUMMER},
+    {"-e", A_FLOAT, OFF(fEps), OFF(bEps), 0},
+    {"-cx", A_FLOAT, OFF(fCenter[0]), 0, 0},
+    {"-cy", A_FLOAT, OFF(fCenter[1]), 0, 0},
+    {"-cz", A_FLOAT, OFF(fCenter[2]), 0, 0},
+    {"-o", A_STR, OFF(achName), 0, 0},
+    {"-ray", A_FLAG, OFF(bOutRay), 0, 1},
+    {"-den", A_FLAG, OFF(bOutDens), 0, 1},
+    {"-stats", A_FLAG, OFF(bOutStats), 0, 1},
+    {"-diag", A_FLAG, OFF(bOutDiag), 0, 1},
+    {"-std", A_FLAG, OFF(bStandard), 0, 1},
+    {"-gpu", A_INT, OFF(iDevice), 0, 0},
+};
+
+static void parse_args(int argc, char **argv, options *o)
+{
+	int i = 1, j;
+	size_t k;
+	memset(o, 0, sizeof *o);
+	/* defaults, main.c:86-136 */
+	o->Omega0 = 1.0f;
+	o->G = 1.0f;
+	o->nSmooth = 64;
+	o->fTempMax = FLT_MAX;
+	o->fMassMax = FLT_MAX;
+	o->nMembers = 8;
+	o->nMaxMembers = INT_MAX;
+	o->iSoftType = SKIDGPU_SPLINE;
+	for (j = 0; j < 3; ++j) o->fPeriod[j] = FLT_MAX;
+	strcpy(o->achName, "skid");
+	while (i < argc) {
+		const char *a = argv[i];
+		int matched = 0;
+		/* -p and -c set all three axes at once (main.c:273-289) */
+		if (!strcmp(a, "-p") || !strcmp(a, "-c")) {
+			float v;
+			if (++i >= argc) usage();
+			v = atof(argv[i++]);
+			for (j = 0; j < 3; ++j) (a[1] == 'p' ? o->fPeriod : o->fCenter)[j] = v;
+			if (a[1] == 'p') o->bPeriodic = 1;
+			continue;
+		}
+		for (k = 0; k < sizeof g_opts / sizeof g_opts[0]; ++k) {
+			const optdef *d = &g_opts[k];
+			char *base = (char *)o;
+			if (strcmp(a, d->name)) continue;
+			matched = 1;
+			++i;
+			if (d->kind == A_FLAG) {
+				*(int *)(base + d->off) = d->flagval;
+			} else {
+				if (i >= argc) usage();
+				if (d->kind == A_FLOAT) *(float *)(base + d->off) = atof(argv[i]);
+				else if (d->kind == A_INT) *(int *)(base + d->off) = atoi(argv[i]);
+				else {
+					strncpy(base + d->off, argv[i], 255);
+					(base + d->off)[255] = 0;
+				}
+				++i;
+			}
+			if (d->off_set) *(int *)(base + d->off_set) = 1;
+			break;
+		}
+		if (!matched) usage();
+	}
+	if (!o->bTau) usage(); /* main.c:339 */
+	if (!o->bCvg) o->fCvg = 0.5 * o->fTau;
+	if (!o->bScoop) o->fScoop = 2.0 * o->fTau;
+}
+
+static void log_cb(void *user, int kind, int iter, int nActive, int nScatter)
+{
+	(void)user;
+	if (kind == 0) printf("Ittr:%d nActive:%d nScatter:%d\n", iter, nActive, nScatter);
+	else printf("Microstep:%d nScatter:%d\n", iter, nScatter);
+	fflush(stdout);
+}
+
+static void die(skidgpu_ctx *ctx, const char *what)
+{
+	fprintf(stderr, "ERROR: %s: %s\n", what, skidgpu_last_error(ctx));
+	exit(1);
+}
+
+static void print_time(const char *label, double ms)
+{
+	long us = (long)(ms * 1000.0 + 0.5);
+	printf("%s%ld.%06ld\n", label, us / 1000000, us % 1000000);
+}
+
+int main(int argc, char **argv)
+{
+	options o;
+	snapshot s;
+	skidgpu_ctx *ctx = NULL;
+	skidgpu_pgroup *cat = NULL;
+	int *piGroup = NULL;
+	float *rho = NULL;
+	float fStep;
+	int nGroup = 1, nMove = 0, nIttr = 0, nUnbound = 0, nBefore = 0, nExtra = 0;
+	char achFile[300];
+
+	printf("SKID v1.4.1 (B200 GPU hot path): group finder compatible with SKID v1.4.1, Stadel 2000\n");
+	parse_args(argc, argv, &o);
+	fStep = 0.5 * o.fCvg; /* main.c:345 */
+
+	if (tipsy_read(stdin, o.bStandard, &s)) {
+		fprintf(stderr, "ERROR: could not read a TIPSY %s binary from stdin\n", o.bStandard ? "standard" : "native");
+		return 1;
+	}
+	printf("nDark:%d nGas:%d nStar:%d\n", s.nDark, s.nGas, s.nStar);
+	fflush(stdout);
+
+	if (skidgpu_create(&ctx, o.iDevice, o.fPeriod, o.fCenter, o.bPeriodic, o.bOutDiag)) die(NULL, "skidgpu_create");
+	if (skidgpu_set_particles(ctx, s.p, s.n, s.nGas, s.nDark, s.nStar)) die(ctx, "skidgpu_set_particles");
+	piGroup = (int *)calloc((size_t)s.n, sizeof(int));
+	rho = (float *)calloc((size_t)s.n, sizeof(float));
+
+	if (o.bUnbindOnly) {
+		/* main.c:349-373: strip a trailing .grp, read <name>.grp and, if present, <name>.gtp */
+		size_t len = strlen(o.achGroup);
+		int rc;
+		if (len >= 4 && !strcmp(o.achGroup + len - 4, ".grp")) o.achGroup[len - 4] = 0;
+		snprintf(achFile, sizeof achFile, "%s.grp", o.achGroup);
+		nGroup = grp_read(achFile, s.n, piGroup);
+		if (nGroup < 0) return 1;
+		cat = (skidgpu_pgroup *)calloc((size_t)nGroup + 1, sizeof(skidgpu_pgroup));
+		snprintf(achFile, sizeof achFile, "%s.gtp", o.achGroup);
+		rc = gtp_read(achFile, o.bStandard, nGroup, cat);
+		if (rc < 0) return 1;
+		if (skidgpu_set_groups(ctx, piGroup, nGroup, rc ? cat : NULL)) die(ctx, "skidgpu_set_groups");
+	} else {
+		int *mvOrder = NULL;
+		float *mvR = NULL;
+		if (skidgpu_density(ctx, o.nSmooth, o.bGasAndDark, o.bGasOnly, rho, NULL, &nExtra)) die(ctx, "skidgpu_density");
+		if (o.bPeriodic) printf("nExtraScat:%d\n", nExtra);
+		if (o.bOutDens) {
+			snprintf(achFile, sizeof achFile, "%s.den", o.achName);
+			out_density(achFile, s.n, rho);
+		}
+		if (skidgpu_move(ctx, o.fDensMin, o.fTempMax, o.fMassMax, o.fCvg, fStep, o.bForceInitialCut, o.bNoPrune,
+		                 log_cb, NULL, &nMove, &nIttr))
+			die(ctx, "skidgpu_move");
+		if (skidgpu_fof(ctx, o.fTau, &nGroup)) die(ctx, "skidgpu_fof");
+		if (skidgpu_microstep(ctx, PRUNE_STEPS, MICRO_STEP * fStep, log_cb, NULL)) die(ctx, "skidgpu_microstep");
+		if (o.bOutRay) {
+			mvOrder = (int *)malloc((size_t)(nMove ? nMove : 1) * sizeof(int));
+			mvR = (float *)malloc((size_t)(nMove ? nMove : 1) * 3 * sizeof(float));
+			if (skidgpu_get_moved(ctx, mvOrder, mvR)) die(ctx, "skidgpu_get_moved");
+			snprintf(achFile, sizeof achFile, "%s.ray", o.achName);
+			out_vector(achFile, &s, nMove, mvOrder, mvR, o.fPeriod);
+			free(mvOrder);
+			free(mvR);
+		}
+		cat = (skidgpu_pgroup *)calloc((size_t)nGroup + 1, sizeof(skidgpu_pgroup));
+		if (skidgpu_centers(ctx, NULL, NULL)) die(ctx, "skidgpu_centers");
+	}
+	/* kdSetUniverse / kdSetSoft / kdUnbind / kdTooSmall (main.c:459-471) */
+	if (o.bEps && skidgpu_set_soft(ctx, o.fEps)) die(ctx, "skidgpu_set_soft");
+	{
+		const float fShift = 1.0 / (1.0 + o.z);
+		const double dHub = cosmo_exp2hub(fShift, o.H0, o.Omega0, o.Lambda, 0.0, o.fQuintess);
+		const double fCosmo = fShift * dHub;
+		if (skidgpu_unbind(ctx, o.G, o.z, fCosmo, o.iSoftType, o.fScoop, o.bNoUnbind, o.nMaxMembers, o.nMembers,
+		                   piGroup, cat, &nGroup, &nUnbound, &nBefore))
+			die(ctx, "skidgpu_unbind");
+		printf("Groups before Unbind:%d\n", nBefore);
+		printf("Number of particles Unbound:%d\n", nUnbound);
+		printf("Number of Groups:%d\n", nGroup - 1);
+		fflush(stdout);
+		snprintf(achFile, sizeof achFile, "%s.grp", o.achName);
+		out_group(achFile, s.n, piGroup);
+		snprintf(achFile, sizeof achFile, "%s.gtp", o.achName);
+		out_gtp(achFile, o.bStandard, s.time, nGroup, cat);
+		if (o.bOutStats) {
+			snprintf(achFile, sizeof achFile, "%s.stat", o.achName);
+			out_stats(achFile, &s, rho, piGroup, nGroup, cat, o.fPeriod, o.G, o.z, fCosmo, o.fDensMin, o.fTempMax);
+		}
+	}
+	printf("SKID GPU Time:\n");
+	if (!o.bUnbindOnly) {
+		print_time("   Initial Density:    ", skidgpu_stage_ms(ctx, 0));
+		print_time("   Moving Particles:   ", skidgpu_stage_ms(ctx, 1));
+		print_time("   Friends of Friends: ", skidgpu_stage_ms(ctx, 2));
+		print_time("   Microstepping:      ", skidgpu_stage_ms(ctx, 3));
+	}
+	if (!o.bNoUnbind) print_time("   Unbinding:          ", skidgpu_stage_ms(ctx, 5));
+	fflush(stdout);
+	skidgpu_destroy(ctx);
+	free(piGroup);
+	free(rho);
+	free(cat);
+	free(s.p);
+	return 0;
+}

@@ -8,7 +8,7 @@ import time
 
 import numpy as np
 
-from .tipsy import PGROUP_DTYPE
+from skid_b200.tipsy import PGROUP_DTYPE
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")

@@ -2,10 +2,13 @@
 #include "ctx.cuh"
 #include <algorithm>
 
+cudaStream_t g_skid_stream = 0;
+
 #define API_BEGIN(ctx)                                                                                 \
 	if (!(ctx)) return SKIDGPU_ERR;                                                                \
 	try {                                                                                          \
-		CK(cudaSetDevice((ctx)->device));
+		CK(cudaSetDevice((ctx)->device));                                                      \
+		g_skid_stream = (ctx)->stream;
 #define API_END(ctx)                                                                                   \
 	}                                                                                              \
 	catch (const std::exception &e)                                                                \
@@ -44,6 +47,12 @@ extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPerio
 		c->bPeriodic = bPeriodic;
 		c->bDiag = bDiag;
 		CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		{ // keep freed blocks cached in the stream-ordered pool (DevBuf, common.cuh)
+			cudaMemPool_t pool;
+			unsigned long long keep = ~0ull;
+			CK(cudaDeviceGetDefaultMemPool(&pool, device));
+			CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+		}
 		CK(cudaEventCreate(&c->ev0));
 		CK(cudaEventCreate(&c->ev1));
 		*pctx = c;
@@ -64,8 +73,13 @@ extern "C" void skidgpu_destroy(skidgpu_ctx *ctx)
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	cudaStream_t s = ctx->stream;
-	delete ctx;
-	if (s) cudaStreamDestroy(s);
+	g_skid_stream = s;
+	delete ctx; // DevBuf destructors free on s
+	if (s) {
+		cudaStreamSynchronize(s);
+		cudaStreamDestroy(s);
+	}
+	g_skid_stream = 0;
 }
 
 extern "C" const char *skidgpu_last_error(skidgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }

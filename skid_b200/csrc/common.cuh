@@ -35,7 +35,10 @@ extern long long g_skid_launches;
 		CK(cudaGetLastError());                                                       \
 	} while (0)
 
-// Grow-only device buffer.
+// Grow-only device buffer, stream-ordered: cudaMallocAsync/cudaFreeAsync on the calling context's
+// stream (set by every API entry point) from the device's default pool, whose release threshold
+// skidgpu_create raises so that freed blocks stay cached - steady state does no driver allocation.
+extern cudaStream_t g_skid_stream;
 template <class T> struct DevBuf {
 	T *p = nullptr;
 	size_t cap = 0;
@@ -45,7 +48,7 @@ template <class T> struct DevBuf {
 	~DevBuf() { release(); }
 	void release()
 	{
-		if (p) cudaFree(p);
+		if (p) cudaFreeAsync(p, g_skid_stream);
 		p = nullptr;
 		cap = 0;
 	}
@@ -54,7 +57,7 @@ template <class T> struct DevBuf {
 		if (n > cap) {
 			release();
 			size_t want = n + n / 16 + 64;
-			CK(cudaMalloc((void **)&p, want * sizeof(T)));
+			CK(cudaMallocAsync((void **)&p, want * sizeof(T), g_skid_stream));
 			cap = want;
 		}
 		return p;

@@ -20,7 +20,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from skid_b200 import refdump, tipsy  # noqa: E402
+from oracle import refdump  # noqa: E402
+from skid_b200 import tipsy  # noqa: E402
 
 DEMO_ARGS = ["-std", "-tau", "9e-4", "-s", "64", "-d", "170", "-m", "8", "-H", "2.8944", "-p", "1",
              "-ray", "-den", "-stats"]

@@ -12,7 +12,7 @@ import pytest
 
 from conftest import DEMO
 from skid_b200 import api
-from skid_b200.refdump import canonical_labels
+from oracle.refdump import canonical_labels
 
 pytestmark = pytest.mark.gpu
 

@@ -1,0 +1,154 @@
+"""Pins the oracle (oracle/skid_oracle.c, the CPU restatement) against golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py), stage by stage on config 1 (the demo).
+CPU only; the whole file runs in about a minute."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import DEMO, ROOT
+
+sys.path.insert(0, ROOT)
+
+
+@pytest.fixture(scope="module")
+def orc():
+    subprocess.run(["make", "-C", ROOT, "oracle/liboracle.so"], check=True, capture_output=True)
+    from oracle import orc as o
+    o.lib()
+    return o
+
+
+@pytest.fixture(scope="module")
+def knn(orc, demo_input):
+    p = demo_input[0]
+    return orc.knn_density(p["r"], p["fMass"], 64, 1.0, want_nbr=True)
+
+
+def test_oracle_knn_ball2_bitwise(knn, demo_golden):
+    ball2 = knn[0]
+    assert np.array_equal(ball2.view(np.uint32), demo_golden["ball2"].view(np.uint32))
+
+
+def test_oracle_knn_neighbor_sets(knn, demo_golden):
+    ball2, _, nbr, d2 = knn
+    for row, i in enumerate(demo_golden["knn_sample"]):
+        ref = set(demo_golden["knn_nbr"][row][demo_golden["knn_d2"][row] < ball2[i]].tolist())
+        mine = set(nbr[i][d2[i] < ball2[i]].tolist())
+        assert mine == ref, i
+
+
+def test_oracle_density(knn, demo_golden):
+    rho = knn[1].astype(np.float64)
+    ref = demo_golden["density"].astype(np.float64)
+    assert (np.abs(rho - ref) / ref).max() <= 1e-5
+
+
+def test_oracle_replicas(orc, demo_input, demo_golden):
+    p = demo_input[0]
+    src, rp = orc.replicas(p["r"], demo_golden["ball2"], 1.0)
+    assert len(src) == int(demo_golden["nExtraScat"]) == 8300
+
+
+@pytest.fixture(scope="module")
+def entities(orc, demo_input, demo_golden):
+    p = demo_input[0]
+    src, rp = orc.replicas(p["r"], demo_golden["ball2"], 1.0)
+    epos = np.concatenate([p["r"], rp])
+    idx = np.concatenate([np.arange(len(p)), src])
+    return dict(pos=epos, ball2=demo_golden["ball2"][idx], mass=p["fMass"][idx], rho=demo_golden["density"][idx],
+                src=idx, nOrig=len(p))
+
+
+def test_oracle_step0_gradient_and_cut(orc, demo_input, demo_golden, entities):
+    p = demo_input[0]
+    movers = np.nonzero(demo_golden["density"] >= np.float32(DEMO["fDensMin"]))[0]
+    assert len(movers) == len(demo_golden["step0_iOrder"]) == 12190
+    acc, touched, fsd = orc.gradient(entities["pos"], entities["ball2"], entities["mass"], entities["rho"],
+                                     p["r"][movers])
+    ref = np.zeros((len(p), 3))
+    ref[demo_golden["step0_iOrder"]] = demo_golden["step0_a"]
+    da = np.linalg.norm(acc - ref[movers], axis=1)
+    na = np.linalg.norm(ref[movers], axis=1)
+    assert np.percentile(da / na, 99) < 2e-5 and (da / na).max() < 5e-4
+    # initial cut + ScatterCut: touched and rho >= fScatDens
+    alive = (touched != 0) & (entities["rho"] >= np.float32(fsd))
+    n = entities["nOrig"]
+    ref_alive = np.unpackbits(demo_golden["step0_alive"])[:n]
+    assert np.array_equal(alive[:n].astype(np.uint8), ref_alive)
+    assert int(alive[n:].sum()) == int(demo_golden["step0_nReplicaAlive"])
+    assert int(alive.sum()) == int(demo_golden["ittr"][0][2])  # nScatter of "Ittr:0" = 20891
+
+
+def test_oracle_fof_on_reference_positions(orc, demo_golden):
+    lab, g = orc.fof(demo_golden["fof_r"], float(np.float32(DEMO["tau"])), 1.0)
+    assert g == 120
+    from oracle.refdump import canonical_labels
+    assert np.array_equal(canonical_labels(lab), canonical_labels(demo_golden["fof_group"]))
+
+
+def test_oracle_move_loop_then_fof(orc, demo_input, demo_golden, entities):
+    """The whole flow loop of the restatement reproduces the reference's Ittr trace and FoF partition."""
+    p = demo_input[0]
+    movers = np.nonzero(demo_golden["density"] >= np.float32(DEMO["fDensMin"]))[0]
+    tau = float(np.float32(DEMO["tau"]))
+    fCvg = float(np.float32(0.5 * tau))
+    fStep = float(np.float32(0.5 * fCvg))
+    r = orc.move_loop(entities["pos"], entities["ball2"], entities["mass"], entities["rho"], p["r"][movers], 1.0,
+                      (0, 0, 0), fCvg, fStep, bInitial=True)
+    ref = demo_golden["ittr"]
+    assert (r["nActive"][0], r["nScatter"][0]) == (ref[0][1], ref[0][2])
+    assert abs(r["nIttr"] - len(ref)) <= 1
+    m = min(r["nIttr"], len(ref))
+    assert np.all(np.abs(r["nActive"][:m] - ref[:m, 1]) <= 0.01 * len(movers))
+    lab, g = orc.fof(r["converged"], tau, 1.0)
+    assert g == 120
+    from oracle.refdump import canonical_labels
+    full = np.zeros(len(p), np.int64)
+    full[movers] = lab
+    ref_full = np.zeros(len(p), np.int64)
+    ref_full[demo_golden["fof_iOrder"]] = demo_golden["fof_group"]
+    assert np.array_equal(canonical_labels(full), canonical_labels(ref_full))
+    # moved positions after the micro steps vs the reference's .ray
+    d = r["final"].astype(np.float64) - p["r"][movers]
+    d -= np.round(d)
+    err = np.abs(d - demo_golden["ray"][movers]).max(axis=1)
+    assert np.percentile(err, 99) < 5e-6
+
+
+def test_oracle_unbind(orc, demo_input, demo_golden):
+    """kdUnbind restated: run every pre-unbind group of the reference (dump 'ub0') through the oracle."""
+    from skid_b200 import api
+    p = demo_input[0]
+    grp0, cat0 = demo_golden["ub0_grp"], demo_golden["ub0_cat"]
+    grp1, cat1 = demo_golden["ub1_grp"], demo_golden["ub1_cat"]
+    tau = float(np.float32(DEMO["tau"]))
+    fScoop2 = np.float32(np.float32(2.0 * tau) ** 2)
+    fCosmo = float(np.float32(1.0 * api.csmExp2Hub(1.0, float(np.float32(DEMO["H0"])), 1.0, 0.0)))
+    loose = np.nonzero(grp0 == 0)[0]
+    total_removed, exact_groups = 0, 0
+    for g in range(1, len(cat0)):
+        mem = np.nonzero(grp0 == g)[0]
+        rel = cat0["rel"][g]
+        dr = (p["r"][mem] - rel).astype(np.float32)
+        dr = np.where(dr > 0.5, dr - 1, dr)
+        dr = np.where(dr <= -0.5, dr + 1, dr).astype(np.float32)
+        # scoop sources: ungrouped particles within fScoop of the density centre (min image)
+        dc = p["r"][loose] - cat0["rCenter"][g]
+        dc -= np.round(dc)
+        sc = loose[(dc.astype(np.float32) ** 2).sum(axis=1) < fScoop2]
+        sr = (p["r"][sc] - rel).astype(np.float32)
+        sr = np.where(sr > 0.5, sr - 1, sr)
+        sr = np.where(sr <= -0.5, sr + 1, sr).astype(np.float32)
+        k, removed, bm, vcm = orc.unbind_group(dr, p["v"][mem], p["fMass"][mem], p["fSoft"][mem], sr, p["fMass"][sc],
+                                               p["fSoft"][sc], 1.0, 0.0, fCosmo)
+        total_removed += k
+        ref_removed = grp1[mem] == 0
+        if np.array_equal(removed.astype(bool), ref_removed):
+            exact_groups += 1
+            if bm > 0:
+                assert abs(bm - cat1["fMass"][g]) <= 1e-4 * cat1["fMass"][g]
+    assert abs(total_removed - int(demo_golden["nUnbound"])) <= 20     # 4134
+    assert exact_groups >= 100                                           # 105/120 identical
