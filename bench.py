@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py - SKID group-finding hot path on B200 (BASELINE.json metric: particles grouped/s,
+density + move + group + unbind, at 2^24).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the whole hot path (tree + kNN density, move-to-convergence, FoF, micro
+steps, centres, unbinding, too-small removal) over one synthetic snapshot.  Workload at N=1:
+BASELINE.json configs[2] - synthetic gas+dark box, 2^24 particles, moving both species (-gd),
+Lambda cosmology, unbinding on.  N>1 (torchrun, one rank per GPU): every rank
+groups its own snapshot of the same configuration (independent snapshots; no data-path collective;
+weak scaling) - see DESIGN.md "multi-GPU".
+
+value     = particles / device time of the K timed steps with the snapshot already in HBM
+            (CUDA events on the context's stream, max over ranks).
+e2e       = same metric through the C-ABI with HOST buffers: pinned AoS snapshot -> device inside the
+            timed region, labels + catalogue read back every step.
+roofline  = the dominant kernel (gradient walk + move): algorithmic bytes (24*C+24 B per
+            mover-step, C = 85) / its device time measured inside this run.
+cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref/skid_ref, serial: 1 core) on
+            a bounded sample of the same generator (2^17 particles), timed on this box's host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particles grouped/sec (density+move+group+unbind)"
+UNIT = "particles/s"
+BYTES_PER_MOVER_STEP = 24 * 85 + 24  # SURVEY.md 8d / DESIGN.md: 24 B per containing scatterer (C = 85) + 24 B mover r/w
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4) if r[5 + k].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference_sample(kind, log2n, seed, noprune=False):
+    """Time the unmodified reference (serial) on a bounded sample.  Returns (particles/s, info)."""
+    from oracle import refdump
+    from skid_b200 import synth
+    if not refdump.have_ref():
+        raise RuntimeError("oracle/_ref/skid_ref not built (run `make ref` in the build container)")
+    snap = synth.make_box(1 << log2n, seed=seed, kind=kind)
+    with tempfile.TemporaryDirectory() as td:
+        f = os.path.join(td, "in.std")
+        synth.write_std(snap, f)
+        out, wall = refdump.run_ref(f, snap["ref_args"], os.path.join(td, "ref"), noprune=noprune)
+    log = refdump.parse_log(out)
+    stages = sum(log["times"].values())  # the reference's own "SKID CPU Time" lines (user CPU, I/O excluded)
+    return (1 << log2n) / stages, dict(wall_s=wall, stage_s=stages, times=log["times"], groups=log.get("nGroup"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=24, help="particles = 2^log2n (BASELINE metric is quoted at 24)")
+    ap.add_argument("--kind", default="gasdark", choices=["dark", "gasdark", "massive"])
+    ap.add_argument("--cpu-log2n", type=int, default=17, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"synthetic {'gas+dark' if a.kind == 'gasdark' else a.kind} box 2^{a.log2n} particles, periodic L=1, "
+                f"moving both species, Lambda cosmology, unbinding on (BASELINE configs[2])"
+                if a.kind == "gasdark" else f"synthetic {a.kind} box 2^{a.log2n} particles, periodic L=1")
+
+    # ------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        W = max(a.warmup, 0)
+        vals = []
+        info = {}
+        for it in range(W + a.steps):
+            v, info = run_reference_sample(a.kind, a.cpu_log2n, seed=7)
+            if it >= W:
+                vals.append((1 << a.cpu_log2n) / v)
+        sec = float(np.mean(vals))
+        value = (1 << a.cpu_log2n) / sec
+        sample = (f"2^{a.cpu_log2n}-particle box of the same generator/flags (full 2^{a.log2n} needs ~{140e-6 * (1 << a.log2n) / 60:.0f} "
+                  f"CPU-minutes); time = sum of the reference's own stage timers")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_detail": info,
+        }))
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    from skid_b200 import api, synth
+    from skid_b200.tipsy import PINIT_DTYPE
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the B200 arm has no CPU fallback", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = 1 << a.log2n
+    snap = synth.make_box(n, seed=7 + rank, kind=a.kind)
+    fl = snap["flags"]
+    p = snap["pinit"]
+    # pinned host AoS (e2e leg) and device SoA (device-resident leg)
+    pin = torch.empty(n * PINIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    host_aos = pin.numpy().view(PINIT_DTYPE)
+    host_aos[:] = p
+    cols = [p["r"][:, 0], p["r"][:, 1], p["r"][:, 2], p["v"][:, 0], p["v"][:, 1], p["v"][:, 2], p["fMass"], p["fSoft"],
+            p["fTemp"]]
+    dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for c in cols]
+    torch.cuda.synchronize()
+
+    per = (fl["period"],) * 3
+    sk = api.SkidGPU(per, (0.0, 0.0, 0.0), bPeriodic=True, device=local)
+    tau = float(np.float32(fl["tau"]))
+    fCvg = float(np.float32(0.5 * tau))
+    fScoop = float(np.float32(2.0 * tau))
+    fStep = float(np.float32(0.5 * fCvg))
+    f32 = lambda v: float(np.float32(v))
+    z = f32(fl.get("z", 0.0))
+    a32 = f32(1.0 / (1.0 + z))
+    fCosmo = a32 * api.csmExp2Hub(a32, f32(fl["H0"]), f32(fl.get("Omega0", 1.0)), f32(fl.get("Lambda", 0.0)))
+
+    def one_pass(host):
+        sk.log = []
+        if host:
+            sk.set_particles(host_aos, snap["nGas"], snap["nDark"], snap["nStar"])
+        else:
+            sk.set_particles_dev([t.data_ptr() for t in dev], n, snap["nGas"], snap["nDark"], snap["nStar"])
+        sk.smDensityInit(fl["nSmooth"], fl.get("bGasAndDark", False), False, want_arrays=False)
+        sk.move(fl["fDensMin"], fl.get("fTempMax", api.FLT_MAX), api.FLT_MAX, fCvg, fStep)
+        sk.kdFoF(tau)
+        sk.microstep(5, f32(0.1 * fStep))
+        sk.kdCalcCenter(fetch=False)
+        grp, cat, nUnb, nBefore = sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX, fl["nMembers"])
+        return grp, cat, nUnb, nBefore
+
+    stream = torch.cuda.ExternalStream(sk.stream(), device=torch.device("cuda", local))
+
+    def timed(host, steps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        stats = dict(mover_steps=0, move_kernel_ms=0.0, move_launches=0, knn_ms=0.0, stage_ms={}, groups=0)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = sk.counter(0)
+        ms0 = sk.counter(1)
+        ev0.record(stream)
+        for _ in range(steps):
+            grp, cat, nUnb, nBefore = one_pass(host)
+            kms, kl = sk.kernel_ms(0)
+            stats["move_kernel_ms"] += kms
+            stats["move_launches"] += kl
+            stats["knn_ms"] += sk.kernel_ms(1)[0]
+            for k, v in sk.stage_ms().items():
+                stats["stage_ms"][k] = stats["stage_ms"].get(k, 0.0) + v / steps
+            stats["groups"] = len(cat) - 1
+            stats["groups_before"] = nBefore
+            stats["unbound"] = nUnb
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        stats["launches"] = sk.counter(0) - l0
+        stats["mover_steps"] = sk.counter(1) - ms0
+        stats["nMove"] = sk.nMove
+        stats["d2h"] = grp.nbytes + cat.nbytes
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, stats
+
+    W = max(a.warmup, 3)
+    timed(False, W)                       # warm-up, device-resident inputs
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, st = timed(False, a.steps)
+    clocks = sampler.stop()
+    timed(True, 1)                        # warm the host path (pinned staging, pool growth)
+    ms_e2e, st_e = timed(True, a.steps)
+
+    total_particles = n * world
+    value = total_particles * a.steps / (ms_dev * 1e-3)
+    e2e_value = total_particles * a.steps / (ms_e2e * 1e-3)
+    peak, peak_src = load_peaks()
+    achieved = st["mover_steps"] * BYTES_PER_MOVER_STEP / (st["move_kernel_ms"] * 1e-3) / 1e9 if st["move_kernel_ms"] > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get("k_move_step_dram_bytes_per_launch")
+    except Exception:
+        pass
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "particles_per_gpu": n, "nSmooth": fl["nSmooth"], "tau": tau,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent snapshots, one per GPU",
+                   "l2": "inputs (604 MB SoA at 2^24) larger than the 126 MB L2; no explicit flush",
+                   "movers": st["nMove"], "groups_before_unbind": st["groups_before"], "groups": st["groups"],
+                   "unbound": st["unbound"]},
+        "stage_ms": st["stage_ms"],
+        "knn_queries_per_s": n / (st["knn_ms"] / a.steps * 1e-3) if st["knn_ms"] > 0 else None,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_aos.nbytes),
+                "d2h_bytes_per_step": int(st_e["d2h"]), "ms_per_step": ms_e2e / a.steps},
+        "gpu_launches": int(st["launches"]),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_move_step (gradient walk + move)", "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_mover_step": BYTES_PER_MOVER_STEP,
+                     "mover_steps_per_step": st["mover_steps"] / a.steps,
+                     "launches_per_step": st["move_launches"] / a.steps,
+                     "avg_launch_ms": st["move_kernel_ms"] / max(st["move_launches"], 1),
+                     "share_of_step": st["move_kernel_ms"] / ms_dev},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            v, info = run_reference_sample(a.kind, a.cpu_log2n, seed=7)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                                   "sample": f"unmodified reference (oracle/_ref/skid_ref, serial) on a 2^{a.cpu_log2n}-particle "
+                                             f"box of the same generator/flags; sum of its own stage timers "
+                                             f"{info['stage_s']:.1f} s (wall {info['wall_s']:.1f} s); host has {os.cpu_count()} cores"}
+        except Exception as e:  # the reference binary did not travel
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
+    if rank == 0:
+        print(json.dumps(out))
+    sk.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -161,6 +161,15 @@ double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage);
  * active movers), entity-hit interactions are not counted on the device. */
 long long skidgpu_counter(skidgpu_ctx *ctx, int which); /* 0 launches, 1 mover-steps, 2 kNN queries, 3 unbind pair evaluations */
 
+/* Device time (ms, CUDA events on the context's stream) spent in the dominant kernels during the
+ * last call of their stage: which 0 = gradient-walk/move kernel launches of skidgpu_move (sum),
+ * 1 = the kNN+density kernel of skidgpu_density; *nLaunches (nullable) = launches covered. */
+double skidgpu_kernel_ms(skidgpu_ctx *ctx, int which, int *nLaunches);
+
+/* The CUDA stream (cudaStream_t) all work of this context is issued on, for callers that want to
+ * bracket calls with their own events. */
+void *skidgpu_stream(skidgpu_ctx *ctx);
+
 /* Test hooks for the hand-written device primitives (stable LSD radix sort of (key,val) pairs on
  * the low `bits` key bits; exclusive prefix sum with out[n] = total).  Host arrays in and out. */
 int skidgpu_debug_sort(skidgpu_ctx *ctx, unsigned long long *keys, unsigned int *vals, long long n, int bits);

@@ -32,6 +32,7 @@ EXPORTS = [
     "skidgpu_get_neighbors", "skidgpu_move", "skidgpu_keep_step0", "skidgpu_get_step0", "skidgpu_fof",
     "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_moved_dev", "skidgpu_centers", "skidgpu_set_groups",
     "skidgpu_unbind", "skidgpu_stage_ms", "skidgpu_counter", "skidgpu_debug_sort", "skidgpu_debug_scan",
+    "skidgpu_kernel_ms", "skidgpu_stream",
 ]
 
 
@@ -71,6 +72,10 @@ def load_library():
     lib.skidgpu_stage_ms.restype = d
     lib.skidgpu_counter.argtypes = [vp, i]
     lib.skidgpu_counter.restype = C.c_longlong
+    lib.skidgpu_kernel_ms.argtypes = [vp, i, P(i)]
+    lib.skidgpu_kernel_ms.restype = d
+    lib.skidgpu_stream.argtypes = [vp]
+    lib.skidgpu_stream.restype = vp
     lib.skidgpu_debug_sort.argtypes = [vp, vp, vp, C.c_longlong, i]
     lib.skidgpu_debug_scan.argtypes = [vp, vp, vp, C.c_longlong]
     _lib = lib
@@ -194,7 +199,10 @@ class SkidGPU:
         self._ck(self.lib.skidgpu_get_moved(self.h, _ptr(iord), _ptr(r)))
         return iord, r
 
-    def kdCalcCenter(self):
+    def kdCalcCenter(self, fetch=True):
+        if not fetch:
+            self._ck(self.lib.skidgpu_centers(self.h, None, None))
+            return None, None
         grp = np.empty(self.n, np.int32)
         cat = np.zeros(self.nGroup, PGROUP_DTYPE)
         self._ck(self.lib.skidgpu_centers(self.h, _ptr(grp), _ptr(cat)))
@@ -232,6 +240,14 @@ class SkidGPU:
     def stage_ms(self):
         names = ["density", "move", "fof", "microstep", "centers", "unbind"]
         return {k: self.lib.skidgpu_stage_ms(self.h, j) for j, k in enumerate(names)}
+
+    def kernel_ms(self, which):
+        nl = C.c_int(0)
+        ms = self.lib.skidgpu_kernel_ms(self.h, which, C.byref(nl))
+        return ms, nl.value
+
+    def stream(self):
+        return self.lib.skidgpu_stream(self.h)
 
     def counter(self, which):
         return int(self.lib.skidgpu_counter(self.h, which))

@@ -55,6 +55,8 @@ extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPerio
 		}
 		CK(cudaEventCreate(&c->ev0));
 		CK(cudaEventCreate(&c->ev1));
+		CK(cudaEventCreate(&c->evk0));
+		CK(cudaEventCreate(&c->evk1));
 		*pctx = c;
 	} catch (const std::exception &e) {
 		g_create_err = e.what();
@@ -72,6 +74,8 @@ extern "C" void skidgpu_destroy(skidgpu_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+	if (ctx->evk0) cudaEventDestroy(ctx->evk0);
+	if (ctx->evk1) cudaEventDestroy(ctx->evk1);
 	cudaStream_t s = ctx->stream;
 	g_skid_stream = s;
 	delete ctx; // DevBuf destructors free on s
@@ -355,6 +359,15 @@ extern "C" double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage)
 	if (!ctx || stage < 0 || stage > 5) return -1.0;
 	return ctx->stage_ms[stage];
 }
+
+extern "C" double skidgpu_kernel_ms(skidgpu_ctx *ctx, int which, int *nLaunches)
+{
+	if (!ctx || which < 0 || which > 1) return -1.0;
+	if (nLaunches) *nLaunches = ctx->kernel_launches[which];
+	return ctx->kernel_ms[which];
+}
+
+extern "C" void *skidgpu_stream(skidgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" long long skidgpu_counter(skidgpu_ctx *ctx, int which)
 {

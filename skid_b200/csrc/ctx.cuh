@@ -75,6 +75,35 @@ struct skidgpu_ctx {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double stage_ms[6] = {0, 0, 0, 0, 0, 0};
 	long long nQueries = 0, nPairs = 0;
+	// dominant-kernel timing (skidgpu_kernel_ms)
+	cudaEvent_t evk0 = nullptr, evk1 = nullptr;
+	double kernel_ms[2] = {0, 0};
+	int kernel_launches[2] = {0, 0};
+};
+
+// Brackets a group of launches of one dominant kernel with events; stop() must be called after a
+// stream synchronisation point has been reached (it synchronises on the stop event itself).
+struct KernelTimer {
+	skidgpu_ctx &c;
+	int which;
+	bool open = false;
+	KernelTimer(skidgpu_ctx &c_, int w) : c(c_), which(w) {}
+	void start()
+	{
+		CK(cudaEventRecord(c.evk0, c.stream));
+		open = true;
+	}
+	void stop(int launches)
+	{
+		if (!open) return;
+		CK(cudaEventRecord(c.evk1, c.stream));
+		CK(cudaEventSynchronize(c.evk1));
+		float ms = 0;
+		CK(cudaEventElapsedTime(&ms, c.evk0, c.evk1));
+		c.kernel_ms[which] += ms;
+		c.kernel_launches[which] += launches;
+		open = false;
+	}
 };
 
 // stage entry points (each in its own .cu)

@@ -454,7 +454,12 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	ka.nbr = c.keepNbr ? c.nbr.p : nullptr;
 	ka.nbrD2 = c.keepNbr ? c.nbrD2.p : nullptr;
 	CK(cudaMemsetAsync(ka.rho64, 0, sizeof(double) * m, s));
+	KernelTimer kt(c, 1);
+	c.kernel_ms[1] = 0;
+	c.kernel_launches[1] = 0;
+	kt.start();
 	SK_LAUNCH(k_knn_density, (unsigned)ceil_div(m, KNN_WARPS), KNN_WARPS * 32, 0, s, ka);
+	kt.stop(1);
 	c.nQueries += m;
 	float *rhoA = c.rhoA.alloc(m);
 	SK_LAUNCH(k_density_finish, (unsigned)ceil_div(m, 256), 256, 0, s, m, iordA, ka.rho64, ka.ball2, rhoA, c.rho.p,

@@ -322,15 +322,18 @@ static int count_scatterers(skidgpu_ctx &c)
 	return (int)h;
 }
 
-static void one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
+static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 {
+	int launched = 0;
 	if (c.nActive > 0 && c.nEnt > 0) {
+		launched = 1;
 		sa.act = c.actList.p;
 		sa.nActive = c.nActive;
 		SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
 		c.moverSteps += c.nActive;
 	}
 	SK_LAUNCH(k_update_T, 1, 1, 0, c.stream, c.dT.p, bNoPrune);
+	return launched;
 }
 
 void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
@@ -400,7 +403,11 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		sa.touched = c.entTouched.p;
 	}
 	int nActiveLog = c.nActive;
-	one_step(c, sa, bNoPrune);
+	KernelTimer kt(c, 0);
+	c.kernel_ms[0] = 0;
+	c.kernel_launches[0] = 0;
+	kt.start();
+	kt.stop(one_step(c, sa, bNoPrune));
 	if (bInitial && c.nEnt > 0 && c.nranks == 1)
 		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p);
 	sa.touched = nullptr;
@@ -419,7 +426,10 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	const float fCvg2 = fCvg * fCvg;
 	int nIttr = 1;
 	while (c.nActive) {
-		for (int i = 0; i < 5; ++i) one_step(c, sa, bNoPrune);
+		int nl = 0;
+		kt.start();
+		for (int i = 0; i < 5; ++i) nl += one_step(c, sa, bNoPrune);
+		kt.stop(nl);
 		// kdPruneInactive
 		uint32_t *pf = c.flags.alloc(c.nActive);
 		uint32_t *ps = c.scan.alloc((size_t)c.nActive + 64);
