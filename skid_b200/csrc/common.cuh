@@ -85,9 +85,10 @@ void radix_sort_pairs(uint64_t *keys, uint32_t *vals, size_t n, int bits, Worksp
 // ---------------------------------------------------------------------------------------
 // tree.cu : 32-wide bucket tree over Morton-ordered points
 // ---------------------------------------------------------------------------------------
-#define SK_MAXLEV 7
+#define SK_MAXLEV 10
 struct BoxTree {
 	int n = 0;          // points
+	int leaf = 32, fan = 32; // points per leaf box, children per node
 	int top = 0;        // number of box levels; level 0 = buckets of 32 points
 	int cnt[SK_MAXLEV]; // boxes per level
 	float4 *box[SK_MAXLEV]; // box[l][2*j] = (lo.xyz, aux), box[l][2*j+1] = (hi.xyz, 0)
@@ -106,7 +107,7 @@ void tree_bbox_only(BoxTree &t, const float *x, const float *y, const float *z, 
 // Build the box levels over sorted points pos4[0..n) (xyz used).  infl (nullable): per-point
 // inflation radius (sorted order); aux (nullable): per-point value whose max goes to lo.w.
 void tree_build_boxes(BoxTree &t, const float4 *pos4, const float *infl, const float *aux, int n,
-                      cudaStream_t s);
+                      cudaStream_t s, int leaf = 32, int fan = 32);
 
 // Device-side view passed by value to kernels.
 struct TreeView {
@@ -114,6 +115,7 @@ struct TreeView {
 	int cnt[SK_MAXLEV];
 	int top;
 	int n;
+	int leaf, fan;
 };
 static inline TreeView tree_view(const BoxTree &t)
 {
@@ -124,6 +126,8 @@ static inline TreeView tree_view(const BoxTree &t)
 	}
 	v.top = t.top;
 	v.n = t.n;
+	v.leaf = t.leaf;
+	v.fan = t.fan;
 	return v;
 }
 

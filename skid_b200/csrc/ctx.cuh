@@ -37,10 +37,10 @@ struct skidgpu_ctx {
 	int nEnt = 0, nExtra = 0;
 	DevBuf<float> ex, ey, ez, eInfl, eRhoSorted;
 	DevBuf<float4> entPosU;  // unsorted (x,y,z,ball2)
-	DevBuf<float2> entNRU;   // unsorted (fNorm, rho)
+	DevBuf<float4> entNRU;   // unsorted (4/fBall2, fNorm, rho, 0)
 	DevBuf<uint32_t> entSrcU; // unsorted: sorted-A index | 0x80000000 for a replica
 	DevBuf<float4> entPos;   // sorted (x,y,z,ball2)
-	DevBuf<float2> entNR;    // sorted (fNorm, rhoEff): rhoEff = 0 once cut at step 0
+	DevBuf<float4> entNR;    // sorted (4/fBall2, fNorm, rhoEff, 0): rhoEff = 0 once cut at step 0
 	DevBuf<uint32_t> entSrc;
 	DevBuf<uint8_t> entTouched;
 	BoxTree treeE;
@@ -51,6 +51,10 @@ struct skidgpu_ctx {
 	DevBuf<float> mx, my, mz, rox, roy, roz;
 	DevBuf<int> mOrd; // mover id -> iOrder
 	DevBuf<uint32_t> actList, actList2;
+	DevBuf<uint32_t> mList;            // candidate lists, LIST_CAP per mover (move.cu)
+	DevBuf<float> lx0, ly0, lz0, ldelta, lhmin;
+	DevBuf<int> lcnt;
+	float listInitFactor = 0.3f;
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step

@@ -321,7 +321,7 @@ __device__ __forceinline__ float grad_norm(float ball2, float mass)
 // mode 0: count replicas per particle into cnt[i]; mode 1: write originals + replicas.
 template <int MODE>
 __global__ void __launch_bounds__(256)
-    k_replicas(const RepArgs a, uint32_t *cnt, const uint32_t *scan, float4 *entPos, float2 *entNR,
+    k_replicas(const RepArgs a, uint32_t *cnt, const uint32_t *scan, float4 *entPos, float4 *entNR,
                uint32_t *entSrc, float *ex, float *ey, float *ez, float *einfl)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256)
 		infl = __fmul_ru(__fsqrt_ru(b2), 1.000001f);
 		// original
 		entPos[i] = make_float4(p.x, p.y, p.z, b2);
-		entNR[i] = make_float2(fn, rho);
+		entNR[i] = make_float4(__fdiv_rn(4.0f, b2), fn, rho, 0.0f);
 		entSrc[i] = (uint32_t)i;
 		ex[i] = p.x;
 		ey[i] = p.y;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256)
 					if (d2 < b2) {
 						if (MODE == 1) {
 							entPos[o] = make_float4(x, y, z, b2);
-							entNR[o] = make_float2(fn, rho);
+							entNR[o] = make_float4(__fdiv_rn(4.0f, b2), fn, rho, 0.0f);
 							entSrc[o] = (uint32_t)i | 0x80000000u;
 							ex[o] = x;
 							ey[o] = y;
@@ -374,18 +374,27 @@ __global__ void __launch_bounds__(256)
 }
 
 __global__ void __launch_bounds__(256)
-    k_gather_entities(int m, const uint32_t *perm, const float4 *posU, const float2 *nrU, const uint32_t *srcU,
-                      const float *inflU, float4 *pos, float2 *nr, uint32_t *src, float *infl, float *rho)
+    k_gather_entities(int m, const uint32_t *perm, const float4 *posU, const float4 *nrU, const uint32_t *srcU,
+                      const float *inflU, float4 *pos, float4 *nr, uint32_t *src, float *infl, float *rho)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m) return;
 	uint32_t j = perm[i];
 	pos[i] = posU[j];
-	float2 v = nrU[j];
+	float4 v = nrU[j];
 	nr[i] = v;
 	src[i] = srcU[j];
 	infl[i] = inflU[j];
-	rho[i] = v.y;
+	rho[i] = v.z;
+}
+
+__global__ void k_pad_entities(int ne, float4 *pos, float4 *aux)
+{
+	int i = ne + threadIdx.x;
+	if (threadIdx.x < 64) {
+		pos[i] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, -1.0f);
+		aux[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	}
 }
 
 // ------------------------------------------------------------------ host side of the stage
@@ -493,7 +502,7 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	if (nExtraScat) *nExtraScat = c.nExtra;
 	const int ne = c.nEnt;
 	float4 *posU = c.entPosU.alloc(ne);
-	float2 *nrU = c.entNRU.alloc(ne);
+	float4 *nrU = c.entNRU.alloc(ne);
 	uint32_t *srcU = c.entSrcU.alloc(ne);
 	float *ex = c.ex.alloc(ne), *ey = c.ey.alloc(ne), *ez = c.ez.alloc(ne), *einfl = c.eInfl.alloc(ne);
 	if (!c.bPeriodic)
@@ -505,14 +514,16 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	SK_LAUNCH(k_replicas<1>, (unsigned)ceil_div(m, 256), 256, 0, s, ra, nullptr, scan, posU, nrU, srcU, ex, ey, ez,
 	          einfl);
 	tree_sort_points(c.treeE, ex, ey, ez, ne, c.ws, s);
-	float4 *ep = c.entPos.alloc(ne);
-	float2 *enr = c.entNR.alloc(ne);
+	float4 *ep = c.entPos.alloc(ne + 64);
+	float4 *enr = c.entNR.alloc(ne + 64);
 	uint32_t *esrc = c.entSrc.alloc(ne);
 	float *inflS = c.tmpx.alloc(ne);
 	float *rhoS = c.eRhoSorted.alloc(ne);
 	SK_LAUNCH(k_gather_entities, (unsigned)ceil_div(ne, 256), 256, 0, s, ne, c.treeE.perm.p, posU, nrU, srcU, einfl, ep,
 	          enr, esrc, inflS, rhoS);
-	tree_build_boxes(c.treeE, ep, inflS, rhoS, ne, s);
-	CK(cudaMemsetAsync(c.entTouched.alloc(ne), 0, ne, s));
+	// pad the sorted scatterer arrays to whole leaves with dummies that can never be hit (fBall2 = -1)
+	SK_LAUNCH(k_pad_entities, 1, 64, 0, s, ne, ep, enr);
+	tree_build_boxes(c.treeE, ep, inflS, rhoS, ne, s, 32, 32);
+	CK(cudaMemsetAsync(c.entTouched.alloc(ne + 64), 0, ne + 64, s));
 	tm.stop();
 }

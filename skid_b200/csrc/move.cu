@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(256) k_gather3b(int m, const uint32_t *idx, co
 // movers in Morton order: r = rOld = initial position, mOrd = iOrder (kd.c:653-662)
 __global__ void __launch_bounds__(256)
     k_init_movers(int m, const uint32_t *perm, const uint32_t *fileIdx, const float *x, const float *y,
-                  const float *z, float *mx, float *my, float *mz, float *rox, float *roy, float *roz, int *mOrd)
+                  const float *z, float *mx, float *my, float *mz, float *rox, float *roy, float *roz, int *mOrd,
+                  const float *ball2, float *lhmin, int *lcnt, float initFactor)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m) return;
@@ -84,6 +85,8 @@ __global__ void __launch_bounds__(256)
 	roy[i] = py;
 	roz[i] = pz;
 	mOrd[i] = (int)j;
+	lhmin[i] = initFactor * sqrtf(fmaxf(ball2[j], 0.0f)); // first margin: a fraction of the mover's own ball radius
+	lcnt[i] = -1;
 }
 
 __global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
 struct StepArgs {
 	TreeView tv;
 	const float4 *entPos; // (x,y,z,fBall2)
-	const float2 *entNR;  // (fNorm, rhoEff)
+	const float4 *entNR;  // (4/fBall2, fNorm, rhoEff, 0)
 	uint8_t *touched;     // nullable: set for entities with >= 1 hit (step 0, initial cut)
 	float *mx, *my, *mz;
 	const uint32_t *act;
@@ -106,6 +109,14 @@ struct StepArgs {
 	float L[3];
 	double wrapLo[3], wrapHi[3];
 	float *a0x, *a0y, *a0z; // nullable: keep accelerations
+	// candidate lists (k_move_list): per mover LIST_CAP scatterer indices, list origin, margin,
+	// count (-1 = no valid list), and the smallest containing ball radius seen at the last walk
+	uint32_t *list;
+	float *lx0, *ly0, *lz0, *ldelta, *lhmin;
+	int *lcnt;
+	int walkAlways; // debug (SKIDGPU_LIST_WALK_ALWAYS=1): never use the lists
+	float polShrink, polGrow; // margin feedback (see k_move_list)
+	int polGrowMax;
 };
 
 constexpr int STEP_WARPS = 8;
@@ -159,19 +170,18 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a)
 			float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
 			float d2 = dist2_rn(dx, dy, dz);
 			if (d2 < p.w) {
-				float2 nr = a.entNR[e];
-				if (nr.y >= T) {
+				float4 nr = a.entNR[e];
+				if (nr.z >= T) {
 					// smAccDensity (smooth1.c:447-459)
-					float ih2 = __fdiv_rn(4.0f, p.w);
-					float r2 = __fmul_rn(d2, ih2);
+					float r2 = __fmul_rn(d2, nr.x);
 					float rs = __fsqrt_rn(r2);
 					if (r2 < 1.0f) rs = (float)(-3.0 + 2.25 * (double)rs);
 					else rs = (float)(-3.0 / (double)rs + 3.0 - 0.75 * (double)rs);
-					rs = __fmul_rn(rs, nr.x);
+					rs = __fmul_rn(rs, nr.y);
 					ax = __fadd_rn(ax, __fmul_rn(dx, rs));
 					ay = __fadd_rn(ay, __fmul_rn(dy, rs));
 					az = __fadd_rn(az, __fmul_rn(dz, rs));
-					rmin = fminf(rmin, nr.y);
+					rmin = fminf(rmin, nr.z);
 					if (a.touched) a.touched[e] = 1;
 				}
 			}
@@ -210,6 +220,196 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a)
 	}
 }
 
+// kdMoveParticles (kd.c:711-729) for one mover
+__device__ __forceinline__ void move_one(const StepArgs &a, uint32_t id, float x, float y, float z, float ax, float ay,
+                                         float az)
+{
+	float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+	float ai = (float)sqrt((double)s2);
+	if (ai > 0.0f) ai = (float)((double)a.fStep / sqrt((double)s2));
+	else ai = 0.0f;
+	float r[3] = {__fsub_rn(x, __fmul_rn(ai, ax)), __fsub_rn(y, __fmul_rn(ai, ay)), __fsub_rn(z, __fmul_rn(ai, az))};
+#pragma unroll
+	for (int j = 0; j < 3; ++j) {
+		if ((double)r[j] > a.wrapHi[j]) r[j] = __fsub_rn(r[j], a.L[j]);
+		if ((double)r[j] <= a.wrapLo[j]) r[j] = __fadd_rn(r[j], a.L[j]);
+	}
+	a.mx[id] = r[0];
+	a.my[id] = r[1];
+	a.mz[id] = r[2];
+}
+
+// Default kernel: warp-per-mover walk + per-mover candidate lists ("Verlet lists").
+//
+// ncu on the v1 kernel above (profiles/r01_v1_move_*): issue-bound, ~3600 warp instructions per
+// mover-step, of which ~85 % are tree bookkeeping and misses (1500 scatterers tested for 85 hits).
+// A mover travels exactly fStep (= tau/4) per step while the balls that contain it have radii of
+// many tau, so the set of scatterers that CAN contain it changes slowly.  Each mover therefore keeps
+// the list of scatterers e with |x_e - x0| < h_e + delta found by one tree walk at x0; as long as the
+// mover stays within delta of x0 every scatterer that contains it is in the list (triangle
+// inequality), and a step is just: read the list (1 KB, coalesced), gather those scatterers, run the
+// SAME float32 hit test, accumulate.  When the mover has drifted past delta (or wrapped around the
+// box) the warp walks the tree again, evaluating this step's gradient and emitting the new list in
+// the same pass.  The hit set, the hit test and the pruning rule are exactly those of v1.
+constexpr int LIST_CAP = 384;
+
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_list(const StepArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1u;
+	const int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+	if (wi >= a.nActive) return;
+	const uint32_t id = a.act[wi];
+	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+	const float T = __uint_as_float(a.dT[0]);
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	float rmin = 3.0e38f;
+	uint32_t *list = a.list + (size_t)id * LIST_CAP;
+
+	// smAccDensity (smooth1.c:447-459) for one hit.  Same float32 operations as the reference
+	// (r2 = d2*ih2, rs = sqrt(r2), rs *= fNorm, a += dx*rs, all round-to-nearest, no FMA on the sums);
+	// the spline factor, which the reference evaluates in double and rounds to float, is formed with
+	// one FMA (inner branch, a single rounding of the exact value) or with a float division plus its
+	// exact-remainder correction (outer branch), i.e. to float accuracy without double arithmetic.
+#define ACC_HIT(dx, dy, dz, d2, q)                                                                     \
+	{                                                                                              \
+		const float r2_ = __fmul_rn((d2), (q).x);                                              \
+		const float rs_ = __fsqrt_rn(r2_);                                                     \
+		float g_;                                                                              \
+		if (r2_ < 1.0f) g_ = fmaf(2.25f, rs_, -3.0f);                                          \
+		else {                                                                                 \
+			const float t_ = __fdiv_rn(-3.0f, rs_);                                        \
+			const float c_ = __fdividef(fmaf(-t_, rs_, -3.0f), rs_);                       \
+			g_ = fmaf(-0.75f, rs_, 3.0f + t_) + c_;                                        \
+		}                                                                                      \
+		g_ = __fmul_rn(g_, (q).y);                                                             \
+		ax = __fadd_rn(ax, __fmul_rn((dx), g_));                                               \
+		ay = __fadd_rn(ay, __fmul_rn((dy), g_));                                               \
+		az = __fadd_rn(az, __fmul_rn((dz), g_));                                               \
+		rmin = fminf(rmin, (q).z);                                                             \
+	}
+
+	const int cnt0 = a.lcnt[id];
+	bool useList = false;
+	if (cnt0 >= 0 && !a.walkAlways) {
+		const float ox = x - a.lx0[id], oy = y - a.ly0[id], oz = z - a.lz0[id];
+		const float dl = a.ldelta[id];
+		useList = (ox * ox + oy * oy + oz * oz) * 1.0001f <= dl * dl;
+	}
+	if (useList) {
+		// ---- list path
+		for (int s0 = 0; s0 < cnt0; s0 += 32) {
+			const int s = s0 + lane;
+			if (s < cnt0) {
+				const uint32_t e = list[s];
+				const float4 p = a.entPos[e];
+				// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
+				const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+				const float d2 = dist2_rn(dx, dy, dz);
+				if (d2 < p.w) {
+					const float4 q = a.entNR[e];
+					if (q.z >= T) ACC_HIT(dx, dy, dz, d2, q);
+				}
+			}
+		}
+	} else {
+		// ---- walk path: evaluate this step AND emit the candidate list for the next ones
+		const float delta = fminf(fmaxf(a.lhmin[id], 2.0f * a.fStep), 64.0f * a.fStep); // lhmin = margin to use
+		const float delta2 = delta * delta;
+		int nHit = 0;
+		int cnt = 0;
+		bool overflow = false;
+		int lev = a.tv.top - 1;
+		uint32_t node = 0, mymask = 0;
+		const float bx0 = x - delta, bx1 = x + delta, by0 = y - delta, by1 = y + delta, bz0 = z - delta, bz1 = z + delta;
+#define LIST_TEST_CHILDREN()                                                                           \
+	{                                                                                              \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		float4 lo = bx[0], hi = bx[1];                                                         \
+		bool in_ = bx1 >= lo.x && bx0 <= hi.x && by1 >= lo.y && by0 <= hi.y && bz1 >= lo.z && bz0 <= hi.z && \
+		           lo.w >= T;                                                                  \
+		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+		LIST_TEST_CHILDREN();
+		while (true) {
+			uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
+			if (m == 0) {
+				++lev;
+				if (lev >= a.tv.top) break;
+				node >>= 5;
+				continue;
+			}
+			int c = __ffs(m) - 1;
+			m &= m - 1;
+			if (lane == lev) mymask = m;
+			uint32_t child = node * 32 + c;
+			if (lev > 0) {
+				--lev;
+				node = child;
+				LIST_TEST_CHILDREN();
+				continue;
+			}
+			const uint32_t e = child * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+			const float4 p = a.entPos[e];
+			const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+			const float d2 = dist2_rn(dx, dy, dz);
+			// candidate: can contain the mover while it stays within delta of here, i.e.
+			// d <= h + delta  <=>  u = d2 - h^2 - delta^2 <= 2 h delta  (no square root; 1e-4 slack)
+			const float u = d2 - p.w - delta2;
+			bool cand = p.w > 0.0f && (u <= 0.0f || u * u <= 4.0004f * p.w * delta2);
+			if (cand) {
+				const float4 q = a.entNR[e];
+				cand = q.z >= T; // dead scatterers never come back
+				if (cand && d2 < p.w) {
+					ACC_HIT(dx, dy, dz, d2, q);
+					++nHit;
+					if (a.touched) a.touched[e] = 1;
+				}
+			}
+			const uint32_t cm = __ballot_sync(SK_FULL, cand);
+			const int nc = __popc(cm);
+			if (cnt + nc <= LIST_CAP) {
+				if (cand) list[cnt + __popc(cm & lt)] = e;
+			} else overflow = true;
+			cnt += nc;
+		}
+#undef LIST_TEST_CHILDREN
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) nHit += __shfl_xor_sync(SK_FULL, nHit, o);
+		if (lane == 0) {
+			a.lcnt[id] = overflow ? -1 : cnt;
+			a.lx0[id] = x;
+			a.ly0[id] = y;
+			a.lz0[id] = z;
+			a.ldelta[id] = delta;
+			// feedback on the margin: a walk costs ~15 list steps, so grow the margin while the list
+			// stays short (< 2.5 x the hits and well below the capacity), shrink it when it is long
+			float next = delta;
+			if (overflow || (float)cnt > a.polShrink * nHit + 32.0f) next = 0.6f * delta;
+			else if ((float)cnt < a.polGrow * nHit + 32.0f && cnt < a.polGrowMax) next = 1.5f * delta;
+			a.lhmin[id] = next;
+		}
+	}
+#undef ACC_HIT
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		ax += __shfl_xor_sync(SK_FULL, ax, o);
+		ay += __shfl_xor_sync(SK_FULL, ay, o);
+		az += __shfl_xor_sync(SK_FULL, az, o);
+		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
+	}
+	if (lane == 0) {
+		if (rmin < 3.0e38f) atomicMin(&a.dT[1], __float_as_uint(rmin)); // smooth1.c:460-461 (rho > 0)
+		if (a.a0x) {
+			a.a0x[id] = ax;
+			a.a0y[id] = ay;
+			a.a0z[id] = az;
+		}
+		move_one(a, id, x, y, z, ax, ay, az);
+	}
+}
+
 // After a step: adopt the new threshold (ScatterCut, smooth1.c:509-513).  If nothing was hit the
 // reference's fScatDens stays 0.0 and nothing is cut.
 __global__ void k_update_T(uint32_t *dT, int bNoPrune)
@@ -220,25 +420,25 @@ __global__ void k_update_T(uint32_t *dT, int bNoPrune)
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
-__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float2 *entNR)
+__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float4 *entNR)
 {
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e < nEnt && !touched[e]) entNR[e].y = 0.0f;
+	if (e < nEnt && !touched[e]) entNR[e].z = 0.0f;
 }
 
 // nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517)
-__global__ void __launch_bounds__(256) k_count_scatter(int nEnt, const float2 *entNR, const uint32_t *dT,
+__global__ void __launch_bounds__(256) k_count_scatter(int nEnt, const float4 *entNR, const uint32_t *dT,
                                                        uint32_t *out)
 {
 	float T = __uint_as_float(dT[0]);
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
-	bool alive = e < nEnt && entNR[e].y >= T;
+	bool alive = e < nEnt && entNR[e].z >= T;
 	uint32_t b = __ballot_sync(SK_FULL, alive);
 	if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (uint32_t)__popc(b));
 }
 
 __global__ void __launch_bounds__(256)
-    k_alive_by_order(int nEnt, const float2 *entNR, const uint32_t *entSrc, const int *iordA, const uint32_t *dT,
+    k_alive_by_order(int nEnt, const float4 *entNR, const uint32_t *entSrc, const int *iordA, const uint32_t *dT,
                      uint8_t *alive)
 {
 	float T = __uint_as_float(dT[0]);
@@ -246,7 +446,7 @@ __global__ void __launch_bounds__(256)
 	if (e >= nEnt) return;
 	uint32_t s = entSrc[e];
 	if (s & 0x80000000u) return;
-	alive[iordA[s]] = entNR[e].y >= T ? 1 : 0;
+	alive[iordA[s]] = entNR[e].z >= T ? 1 : 0;
 }
 
 // kdPruneInactive (kd.c:735-793): a mover stays active iff it moved >= fCvg (min image) since the
@@ -307,6 +507,28 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 		sa.wrapLo[d] = (double)c.C[d] - 0.5 * (double)c.L[d]; // kd.c:726
 	}
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
+	sa.list = c.mList.p;
+	sa.lx0 = c.lx0.p;
+	sa.ly0 = c.ly0.p;
+	sa.lz0 = c.lz0.p;
+	sa.ldelta = c.ldelta.p;
+	sa.lhmin = c.lhmin.p;
+	sa.lcnt = c.lcnt.p;
+	static int wa = -1;
+	if (wa < 0) wa = getenv("SKIDGPU_LIST_WALK_ALWAYS") ? 1 : 0;
+	sa.walkAlways = wa;
+	static float pol[4] = {-1, 0, 0, 0};
+	if (pol[0] < 0) {
+		pol[0] = 3.0f;  // shrink when candidates > 3 x hits (+32)
+		pol[1] = 1.5f;  // grow while candidates < 1.5 x hits (+32)
+		pol[2] = 96.f;  // ... and fewer than this (measured sweep: tools/sweep_policy.sh)
+		pol[3] = 0.3f;  // first margin = 0.3 x own ball radius
+		if (const char *e = getenv("SKIDGPU_LIST_POLICY")) sscanf(e, "%f,%f,%f,%f", &pol[0], &pol[1], &pol[2], &pol[3]);
+	}
+	sa.polShrink = pol[0];
+	sa.polGrow = pol[1];
+	sa.polGrowMax = (int)pol[2];
+	c.listInitFactor = pol[3];
 }
 
 static int count_scatterers(skidgpu_ctx &c)
@@ -322,6 +544,19 @@ static int count_scatterers(skidgpu_ctx &c)
 	return (int)h;
 }
 
+// SKIDGPU_MOVE_KERNEL=warp selects the v1 kernel (a tree walk every step; kept for A/B
+// measurements); default = walk + candidate lists.
+bool use_list_kernel();
+bool use_list_kernel()
+{
+	static int v = -1;
+	if (v < 0) {
+		const char *e = getenv("SKIDGPU_MOVE_KERNEL");
+		v = (e && !strcmp(e, "warp")) ? 0 : 1;
+	}
+	return v == 1;
+}
+
 static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 {
 	int launched = 0;
@@ -329,7 +564,10 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 		launched = 1;
 		sa.act = c.actList.p;
 		sa.nActive = c.nActive;
-		SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
+		if (use_list_kernel())
+			SK_LAUNCH(k_move_list, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
+		else
+			SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
 		c.moverSteps += c.nActive;
 	}
 	SK_LAUNCH(k_update_T, 1, 1, 0, c.stream, c.dT.p, bNoPrune);
@@ -345,6 +583,10 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	if (!c.rho.p) throw SkidError("skidgpu_move: skidgpu_density has not run");
 	StageTimer tm(c, 1);
 	c.bNoPrune = bNoPrune;
+	{
+		StepArgs tmp;
+		fill_step_args(c, tmp, fStep); // also reads the list policy (listInitFactor) from the environment
+	}
 
 	// ---- kdInitMove
 	uint32_t *flags = c.flags.alloc(n);
@@ -377,8 +619,15 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.roy.alloc(m);
 		c.roz.alloc(m);
 		c.mOrd.alloc(m);
+		c.lx0.alloc(m);
+		c.ly0.alloc(m);
+		c.lz0.alloc(m);
+		c.ldelta.alloc(m);
+		c.lhmin.alloc(m);
+		c.lcnt.alloc(m);
+		if (use_list_kernel()) c.mList.alloc((size_t)m * LIST_CAP);
 		SK_LAUNCH(k_init_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeM.perm.p, fileIdx, c.x.p, c.y.p,
-		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p);
+		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p, c.ball2.p, c.lhmin.p, c.lcnt.p, c.listInitFactor);
 		c.actList.alloc(m);
 		c.actList2.alloc(m); // fileIdx no longer needed after k_init_movers (same stream)
 		if (c.nActive > 0)

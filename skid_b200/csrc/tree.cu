@@ -118,14 +118,13 @@ void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z
 	radix_sort_pairs(keys, perm, n, 63, ws, s);
 }
 
-// One warp per bucket of 32 sorted points.
+// Leaf boxes: `leaf` consecutive sorted points per leaf (leaf = 8, 16 or 32 lanes of a warp).
 __global__ void __launch_bounds__(256) k_leaf_boxes(const float4 *pos4, const float *infl, const float *aux,
-                                                    int n, float4 *box, int nBoxPadded)
+                                                    int n, float4 *box, int nBoxPadded, int leaf)
 {
-	int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	if (b >= nBoxPadded) return;
-	int lane = threadIdx.x & 31;
-	int i = b * 32 + lane;
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	long long b = i / leaf;
+	if (b >= nBoxPadded) return; // whole groups exit together: nBoxPadded*leaf is a multiple of 32
 	float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
 	float a = -3.0e38f;
 	if (i < n) {
@@ -139,8 +138,7 @@ __global__ void __launch_bounds__(256) k_leaf_boxes(const float4 *pos4, const fl
 		hi[2] = __fadd_ru(p.z, h);
 		if (aux) a = aux[i];
 	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
+	for (int o = leaf >> 1; o > 0; o >>= 1) {
 #pragma unroll
 		for (int d = 0; d < 3; ++d) {
 			lo[d] = fminf(lo[d], __shfl_xor_sync(SK_FULL, lo[d], o));
@@ -148,28 +146,26 @@ __global__ void __launch_bounds__(256) k_leaf_boxes(const float4 *pos4, const fl
 		}
 		a = fmaxf(a, __shfl_xor_sync(SK_FULL, a, o));
 	}
-	if (lane == 0) {
+	if ((i % leaf) == 0) {
 		box[2 * b] = make_float4(lo[0], lo[1], lo[2], a);
 		box[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
 	}
 }
 
-// One warp per parent: union of up to 32 child boxes.
+// Parent boxes: union of `fan` consecutive child boxes (fan = 8 or 32 lanes of a warp).
 __global__ void __launch_bounds__(256) k_upper_boxes(const float4 *child, int nChild, float4 *box,
-                                                     int nBoxPadded)
+                                                     int nBoxPadded, int fan)
 {
-	int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	long long b = c / fan;
 	if (b >= nBoxPadded) return;
-	int lane = threadIdx.x & 31;
-	int c = b * 32 + lane;
 	float4 lo = make_float4(3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f);
 	float4 hi = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.0f);
 	if (c < nChild) {
 		lo = child[2 * c];
 		hi = child[2 * c + 1];
 	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
+	for (int o = fan >> 1; o > 0; o >>= 1) {
 		lo.x = fminf(lo.x, __shfl_xor_sync(SK_FULL, lo.x, o));
 		lo.y = fminf(lo.y, __shfl_xor_sync(SK_FULL, lo.y, o));
 		lo.z = fminf(lo.z, __shfl_xor_sync(SK_FULL, lo.z, o));
@@ -178,27 +174,33 @@ __global__ void __launch_bounds__(256) k_upper_boxes(const float4 *child, int nC
 		hi.y = fmaxf(hi.y, __shfl_xor_sync(SK_FULL, hi.y, o));
 		hi.z = fmaxf(hi.z, __shfl_xor_sync(SK_FULL, hi.z, o));
 	}
-	if (lane == 0) {
+	if ((c % fan) == 0) {
 		box[2 * b] = lo;
 		box[2 * b + 1] = hi;
 	}
 }
 
+// Levels: level 0 = leaves of `leaf` points; a node of level l+1 has `fan` children of level l; the
+// root is implicit (its children are the <= fan boxes of level top-1).  Every level is padded to a
+// multiple of max(fan, 32/leaf...) boxes with empty boxes so traversals never read out of bounds.
 void tree_build_boxes(BoxTree &t, const float4 *pos4, const float *infl, const float *aux, int n,
-                      cudaStream_t s)
+                      cudaStream_t s, int leaf, int fan)
 {
+	if ((leaf != 8 && leaf != 16 && leaf != 32) || (fan != 8 && fan != 32))
+		throw SkidError("tree_build_boxes: unsupported leaf/fan");
 	t.n = n;
-	// level sizes
+	t.leaf = leaf;
+	t.fan = fan;
 	int cnt[SK_MAXLEV], pad[SK_MAXLEV];
 	int top = 0;
-	int c = (int)ceil_div(n > 0 ? n : 1, 32);
+	int c = (int)ceil_div(n > 0 ? n : 1, leaf);
 	while (true) {
 		if (top >= SK_MAXLEV) throw SkidError("tree_build_boxes: too many levels");
 		cnt[top] = c;
-		pad[top] = (int)ceil_div(c, 32) * 32;
+		pad[top] = (int)ceil_div(c, 32) * 32; // multiple of 32 (hence of fan) boxes
 		++top;
-		if (c <= 32) break;
-		c = (int)ceil_div(c, 32);
+		if (c <= fan) break;
+		c = (int)ceil_div(c, fan);
 	}
 	size_t total = 0;
 	for (int l = 0; l < top; ++l) total += 2 * (size_t)pad[l];
@@ -214,9 +216,9 @@ void tree_build_boxes(BoxTree &t, const float4 *pos4, const float *infl, const f
 		off += 2 * (size_t)pad[l];
 	}
 	t.top = top;
-	SK_LAUNCH(k_leaf_boxes, (unsigned)ceil_div((size_t)pad[0] * 32, 256), 256, 0, s, pos4, infl, aux, n,
-	          t.box[0], pad[0]);
+	SK_LAUNCH(k_leaf_boxes, (unsigned)ceil_div((size_t)pad[0] * leaf, 256), 256, 0, s, pos4, infl, aux, n, t.box[0],
+	          pad[0], leaf);
 	for (int l = 1; l < top; ++l)
-		SK_LAUNCH(k_upper_boxes, (unsigned)ceil_div((size_t)pad[l] * 32, 256), 256, 0, s, t.box[l - 1],
-		          cnt[l - 1], t.box[l], pad[l]);
+		SK_LAUNCH(k_upper_boxes, (unsigned)ceil_div((size_t)pad[l] * fan, 256), 256, 0, s, t.box[l - 1], cnt[l - 1],
+		          t.box[l], pad[l], fan);
 }
