@@ -120,6 +120,7 @@ struct KnnArgs {
 	const int *iord;
 	int n, k;
 	float L[3], hL[3];
+	float boxLo[3], boxHi[3]; // the periodic box (centre -+ L/2); +-FLT_MAX when not periodic
 	float *ball2;
 	double *rho64;
 	int *nbr;     // nullable, [nFile*k] by file index
@@ -128,64 +129,46 @@ struct KnnArgs {
 
 constexpr int KNN_WARPS = 8;
 
-__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
+struct KnnQuery {
+	float x0, y0, z0, xp, xm, yp, ym, zp, zm, hx, hy, hz;
+};
+
+// squared distance from the query to point p / to box [lo,hi]; PER = query ball may cross the box faces
+template <bool PER> __device__ __forceinline__ float knn_d2(const KnnQuery &q, const float4 &p)
 {
-	__shared__ uint64_t s_buf[KNN_WARPS][64];
-	__shared__ float s_dist[KNN_WARPS][SK_MAXLEV][32];
-	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (PER)
+		return dist2_rn(minimg_dx(q.x0, q.xp, q.xm, q.hx, p.x), minimg_dx(q.y0, q.yp, q.ym, q.hy, p.y),
+		                minimg_dx(q.z0, q.zp, q.zm, q.hz, p.z));
+	return dist2_rn(__fsub_rn(q.x0, p.x), __fsub_rn(q.y0, p.y), __fsub_rn(q.z0, p.z));
+}
+template <bool PER> __device__ __forceinline__ float knn_box_d2(const KnnQuery &q, const float4 &lo, const float4 &hi)
+{
+	if (PER)
+		return dist2_rn(axis_gap_periodic(q.x0, q.xp, q.xm, lo.x, hi.x), axis_gap_periodic(q.y0, q.yp, q.ym, lo.y, hi.y),
+		                axis_gap_periodic(q.z0, q.zp, q.zm, lo.z, hi.z));
+	return dist2_rn(axis_gap(q.x0, lo.x, hi.x), axis_gap(q.y0, lo.y, hi.y), axis_gap(q.z0, lo.z, hi.z));
+}
+
+// Tree walk of one query (one warp).  Buckets [skipLo, skipHi] were merged before the walk.
+template <bool PER>
+__device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, uint64_t *s_buf, float (*s_dist)[32],
+                                         int lane, int skipLo, int skipHi, uint64_t &a0, uint64_t &a1, int &cnt,
+                                         float &bound)
+{
 	const uint32_t lt = (1u << lane) - 1u;
-	const int qi = blockIdx.x * KNN_WARPS + w;
-	if (qi >= a.n) return;
 	const int n = a.n, k = a.k;
-	const float4 q = a.pos4[qi];
-	const float x0 = q.x, y0 = q.y, z0 = q.z;
-	const float xp = __fadd_rn(x0, a.L[0]), xm = __fsub_rn(x0, a.L[0]);
-	const float yp = __fadd_rn(y0, a.L[1]), ym = __fsub_rn(y0, a.L[1]);
-	const float zp = __fadd_rn(z0, a.L[2]), zm = __fsub_rn(z0, a.L[2]);
-	const float hx = a.hL[0], hy = a.hL[1], hz = a.hL[2];
-
-	// initial bound: k consecutive points of the Morton order around the query are k distinct
-	// candidates, so the largest of their distances bounds the k-th nearest distance.
-	float bound;
-	{
-		int s0 = qi - (k >> 1);
-		if (s0 > n - k) s0 = n - k;
-		if (s0 < 0) s0 = 0;
-		float bm = 0.0f;
-#pragma unroll
-		for (int r = 0; r < 2; ++r) {
-			int e = r * 32 + lane;
-			if (e < k) {
-				float4 p = a.pos4[s0 + e];
-				float d2 = dist2_rn(minimg_dx(x0, xp, xm, hx, p.x), minimg_dx(y0, yp, ym, hy, p.y),
-				                    minimg_dx(z0, zp, zm, hz, p.z));
-				bm = fmaxf(bm, d2);
-			}
-		}
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(SK_FULL, bm, o));
-		bound = bm;
-	}
-
-	uint64_t a0 = KNN_INF, a1 = KNN_INF;
-	int cnt = 0;
 	int lev = a.tv.top - 1;
 	uint32_t node = 0;
 	uint32_t mymask = 0;
-
 #define KNN_TEST_CHILDREN()                                                                            \
 	{                                                                                              \
 		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
-		float4 lo = bx[0], hi = bx[1];                                                         \
-		float d = dist2_rn(axis_gap_periodic(x0, xp, xm, lo.x, hi.x),                          \
-		                   axis_gap_periodic(y0, yp, ym, lo.y, hi.y),                          \
-		                   axis_gap_periodic(z0, zp, zm, lo.z, hi.z));                         \
-		s_dist[w][lev][lane] = d;                                                              \
+		float d = knn_box_d2<PER>(q, bx[0], bx[1]);                                            \
+		s_dist[lev][lane] = d;                                                                 \
 		uint32_t m_ = __ballot_sync(SK_FULL, d <= bound);                                      \
 		if (lane == lev) mymask = m_;                                                          \
 		__syncwarp();                                                                          \
 	}
-
 	KNN_TEST_CHILDREN();
 	while (true) {
 		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
@@ -198,7 +181,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 		int c = __ffs(m) - 1;
 		m &= m - 1;
 		if (lane == lev) mymask = m;
-		if (s_dist[w][lev][c] > bound) continue;
+		if (s_dist[lev][c] > bound) continue;
 		uint32_t child = node * 32 + c;
 		if (lev > 0) {
 			--lev;
@@ -206,24 +189,24 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 			KNN_TEST_CHILDREN();
 			continue;
 		}
+		if ((int)child >= skipLo && (int)child <= skipHi) continue;
 		// leaf bucket: 32 points, one per lane
 		int idx = (int)child * 32 + lane;
 		bool valid = idx < n;
 		float4 p = a.pos4[valid ? idx : 0];
-		float d2 = dist2_rn(minimg_dx(x0, xp, xm, hx, p.x), minimg_dx(y0, yp, ym, hy, p.y),
-		                    minimg_dx(z0, zp, zm, hz, p.z));
+		float d2 = knn_d2<PER>(q, p);
 		bool hit = valid && d2 <= bound;
 		uint32_t hm = __ballot_sync(SK_FULL, hit);
 		if (hm) {
-			if (hit) s_buf[w][cnt + __popc(hm & lt)] = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
+			if (hit) s_buf[cnt + __popc(hm & lt)] = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
 			cnt += __popc(hm);
 			__syncwarp();
 			if (cnt >= 32) {
-				uint64_t b = s_buf[w][lane];
+				uint64_t b = s_buf[lane];
 				kbest_merge(a0, a1, b, lane);
-				uint64_t t = (lane + 32 < cnt) ? s_buf[w][lane + 32] : KNN_INF;
+				uint64_t t = (lane + 32 < cnt) ? s_buf[lane + 32] : KNN_INF;
 				__syncwarp();
-				s_buf[w][lane] = t;
+				s_buf[lane] = t;
 				__syncwarp();
 				cnt -= 32;
 				uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
@@ -232,6 +215,61 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 		}
 	}
 #undef KNN_TEST_CHILDREN
+}
+
+__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
+{
+	__shared__ uint64_t s_buf[KNN_WARPS][64];
+	__shared__ float s_dist[KNN_WARPS][SK_MAXLEV][32];
+	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int qi = blockIdx.x * KNN_WARPS + w;
+	if (qi >= a.n) return;
+	const int n = a.n, k = a.k;
+	const float4 qp = a.pos4[qi];
+	KnnQuery q;
+	q.x0 = qp.x;
+	q.y0 = qp.y;
+	q.z0 = qp.z;
+	q.xp = __fadd_rn(qp.x, a.L[0]);
+	q.xm = __fsub_rn(qp.x, a.L[0]);
+	q.yp = __fadd_rn(qp.y, a.L[1]);
+	q.ym = __fsub_rn(qp.y, a.L[1]);
+	q.zp = __fadd_rn(qp.z, a.L[2]);
+	q.zm = __fsub_rn(qp.z, a.L[2]);
+	q.hx = a.hL[0];
+	q.hy = a.hL[1];
+	q.hz = a.hL[2];
+
+	// Phase A: the query's own bucket and its two Morton neighbours hold most of the k nearest;
+	// merging them first gives a tight bound (the k-th best of >= 64 real candidates) before the walk.
+	uint64_t a0 = KNN_INF, a1 = KNN_INF;
+	const int nB = (n + 31) >> 5;
+	int b0 = (qi >> 5) - 1;
+	if (b0 > nB - 3) b0 = nB - 3;
+	if (b0 < 0) b0 = 0;
+	const int b1 = b0 + 2 < nB - 1 ? b0 + 2 : nB - 1;
+	for (int b = b0; b <= b1; ++b) {
+		int idx = b * 32 + lane;
+		bool valid = idx < n;
+		float4 p = a.pos4[valid ? idx : 0];
+		float d2 = knn_d2<true>(q, p);
+		uint64_t c = valid ? (((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx) : KNN_INF;
+		kbest_merge(a0, a1, c, lane);
+	}
+	float bound;
+	{
+		uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
+		bound = __uint_as_float((uint32_t)(kth >> 32)); // +inf while fewer than k candidates are known
+	}
+	int cnt = 0;
+	// Phase B: walk the tree for everything else inside the bound.  If the ball cannot reach a face
+	// of the periodic box no image can be closer than the point itself: plain differences are then
+	// bit-identical to the min-image ones and much cheaper.
+	const float r0 = sqrtf(bound) * 1.000001f;
+	const bool per = !(q.x0 - r0 >= a.boxLo[0] && q.x0 + r0 <= a.boxHi[0] && q.y0 - r0 >= a.boxLo[1] &&
+	                   q.y0 + r0 <= a.boxHi[1] && q.z0 - r0 >= a.boxLo[2] && q.z0 + r0 <= a.boxHi[2]);
+	if (per) knn_walk<true>(a, q, s_buf[w], s_dist[w], lane, b0, b1, a0, a1, cnt, bound);
+	else knn_walk<false>(a, q, s_buf[w], s_dist[w], lane, b0, b1, a0, a1, cnt, bound);
 	if (cnt > 0) {
 		uint64_t b = (lane < cnt) ? s_buf[w][lane] : KNN_INF;
 		kbest_merge(a0, a1, b, lane);
@@ -243,7 +281,7 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 	// ---- density (smooth1.c:249-263): every PQ entry except the farthest (pqHead)
 	const float ih2 = __fdiv_rn(4.0f, fBall2);                                          // (float)(4.0/h2)
 	const float fNorm = (float)(0.5 * 0.318309886183790671538 * sqrt((double)ih2) * (double)ih2);
-	const float mi = q.w;
+	const float mi = qp.w;
 	double gsum = 0.0;
 #pragma unroll
 	for (int r = 0; r < 2; ++r) {
@@ -457,6 +495,8 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	for (int d = 0; d < 3; ++d) {
 		ka.L[d] = c.L[d];
 		ka.hL[d] = 0.5f * c.L[d];
+		ka.boxLo[d] = c.bPeriodic ? (float)((double)c.C[d] - 0.5 * (double)c.L[d]) : -3.4e38f;
+		ka.boxHi[d] = c.bPeriodic ? (float)((double)c.C[d] + 0.5 * (double)c.L[d]) : 3.4e38f;
 	}
 	ka.ball2 = c.ball2A.alloc(m);
 	ka.rho64 = c.rho64A.alloc(m);
