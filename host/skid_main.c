@@ -44,6 +44,7 @@ static void usage(void)
 }
 
 typedef struct {
+	int reserved0; /* keeps every real field at a non-zero offset: offset 0 means "no flag field" in g_opts */
 	int bTau, bCvg, bScoop, bEps, bPeriodic, bStandard;
 	int nSmooth, nMembers, nMaxMembers, iSoftType;
 	int bNoUnbind, bGasAndDark, bGasOnly, bUnbindOnly, bForceInitialCut, bNoPrune;

@@ -86,6 +86,26 @@ def test_host_driver_usage_contract(built):
         assert r.returncode == 1 and r.stderr.startswith("USAGE:"), args
 
 
+def test_host_driver_accepts_reference_flags(built, tmp_path):
+    """Every flag of the reference's main.c:140-335 parses; without a GPU the run then stops at
+    skidgpu_create with the 'no CPU fallback' message (never at usage())."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    snap = synth.make_box(512, seed=2)
+    f = tmp_path / "in.std"
+    synth.write_std(snap, str(f))
+    flags = ["-std", "-tau", "9e-4", "-z", "0.5", "-O", "0.3", "-Lambda", "0.7", "-Q", "0", "-G", "1", "-H", "2.8944",
+             "-s", "32", "-d", "170", "-t", "3e4", "-M", "1", "-fic", "-cvg", "4e-4", "-scoop", "2e-3", "-m", "8",
+             "-maxgroup", "100000", "-nu", "-gd", "-go", "-spline", "-plummer", "-e", "1e-3", "-p", "1", "-c", "0",
+             "-cx", "0", "-cy", "0", "-cz", "0", "-o", str(tmp_path / "out"), "-ray", "-den", "-stats", "-diag", "-nsp"]
+    with open(f, "rb") as fin:
+        r = subprocess.run([os.path.join(ROOT, "host", "skid")] + flags, stdin=fin, capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "USAGE" not in r.stderr and "no CPU fallback" in r.stderr
+    assert "nDark:512 nGas:0 nStar:0" in r.stdout
+
+
 def test_golden_fixture_consistency(demo_golden, demo_input):
     p = demo_input[0]
     assert len(p) == 32768 and demo_input[2] == 32768

@@ -1,0 +1,115 @@
+"""End-to-end drop-in check of the C host driver (host/skid): same command line, stdin TIPSY, output
+files as the reference.  Compared against the golden outputs of the unmodified reference on the demo
+and, when oracle/_ref travelled to this box, against the reference binary run live (gas+dark box,
+the -unbind restart path, -nu, -nsp)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from oracle import refdump
+from oracle.refdump import canonical_labels
+from skid_b200 import synth, tipsy
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "host", "skid")
+DEMO_ARGS = ["-std", "-tau", "9e-4", "-s", "64", "-d", "170", "-m", "8", "-H", "2.8944", "-p", "1", "-ray", "-den",
+             "-stats"]
+
+
+def run_skid(tipsy_path, args, prefix):
+    with open(tipsy_path, "rb") as fin:
+        r = subprocess.run([EXE] + [str(a) for a in args] + ["-o", prefix], stdin=fin, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-800:]
+    return r.stdout
+
+
+@pytest.fixture(scope="module")
+def demo_files(tmp_path_factory, demo_input):
+    p, ng, nd, ns, t = demo_input
+    d = tmp_path_factory.mktemp("demo")
+    f = str(d / "dark.std")
+    gas, dark, star = tipsy.pinit_to_records(p, ng, nd, ns)
+    tipsy.write_tipsy(f, t, gas, dark, star, standard=True)
+    out = run_skid(f, DEMO_ARGS, str(d / "dark"))
+    return str(d / "dark"), out
+
+
+def test_demo_stdout_lines(demo_files):
+    _, out = demo_files
+    log = refdump.parse_log(out)
+    assert "nDark:32768 nGas:0 nStar:0" in out
+    assert log["nExtraScat"] == 8300
+    assert log["ittr"][0] == (0, 12190, 20891)
+    assert abs(len(log["ittr"]) - 38) <= 1 and log["ittr"][-1][1] == 0
+    assert len(log["micro"]) == 5
+    assert log["nGroupBefore"] == 120 and log["nGroup"] == 68
+    assert abs(log["nUnbound"] - 4134) <= 20
+
+
+def test_demo_output_files(demo_files, demo_golden, demo_input):
+    pre, _ = demo_files
+    n = 32768
+    den = tipsy.read_array(pre + ".den")
+    assert len(den) == n
+    assert (np.abs(den - demo_golden["density"]) / demo_golden["density"]).max() <= 1e-5
+    grp = tipsy.read_array(pre + ".grp").astype(np.int64)
+    assert grp.max() == 68
+    assert np.mean(canonical_labels(grp) == canonical_labels(demo_golden["grp"])) >= 0.999
+    ray = tipsy.read_vector(pre + ".ray")
+    err = np.abs(ray - demo_golden["ray"]).max(axis=1)
+    assert np.array_equal(ray.any(axis=1), demo_golden["ray"].any(axis=1))   # same set of movers
+    assert np.percentile(err, 99.9) < 2e-5 and err.max() < 2.25e-4
+    gtp = tipsy.read_gtp(pre + ".gtp", standard=True)
+    assert len(gtp["mass"]) == 68 and gtp["time"] == demo_input[4]
+    # catalogue rows match the reference's up to the group numbering: compare as sorted multisets
+    ref = np.sort(demo_golden["gtp_mass"])
+    assert np.allclose(np.sort(gtp["mass"]), ref, rtol=2e-3)
+    assert np.sum(np.abs(np.sort(gtp["mass"]) - ref) <= 1e-4 * ref) >= 60
+    stat = np.loadtxt(pre + ".stat")
+    ref_stat = np.loadtxt(os.path.join(GOLDEN, "demo.stat"))
+    assert stat.shape == ref_stat.shape == (68, 21)
+    assert np.array_equal(stat[:, 0], np.arange(1, 69))
+    for col in (1, 2, 5, 7, 10):  # members, mass, vcirc max, outer vcirc, outer radius
+        assert np.allclose(np.sort(stat[:, col]), np.sort(ref_stat[:, col]), rtol=5e-3), col
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("extra", [[], ["-nu"], ["-plummer", "-e", "0.001"], ["-nsp"]])
+def test_live_reference_gasdark(tmp_path, extra):
+    snap = synth.make_box(1 << 14, seed=11, kind="gasdark")
+    f = str(tmp_path / "in.std")
+    synth.write_std(snap, f)
+    args = snap["ref_args"] + ["-den"]
+    ref_extra = [e for e in extra if e != "-nsp"]
+    out_ref, _ = refdump.run_ref(f, args + ref_extra, str(tmp_path / "ref"), noprune="-nsp" in extra)
+    out = run_skid(f, args + extra, str(tmp_path / "gpu"))
+    a, b = refdump.parse_log(out_ref), refdump.parse_log(out)
+    assert b["ittr"][0] == a["ittr"][0]
+    assert b["nGroupBefore"] == a["nGroupBefore"]
+    assert abs(b["nGroup"] - a["nGroup"]) <= 1
+    den_r, den_g = tipsy.read_array(str(tmp_path / "ref.den")), tipsy.read_array(str(tmp_path / "gpu.den"))
+    assert (np.abs(den_g - den_r) / den_r).max() <= 1e-5
+    gr, gg = tipsy.read_array(str(tmp_path / "ref.grp")), tipsy.read_array(str(tmp_path / "gpu.grp"))
+    assert np.mean(canonical_labels(gr.astype(np.int64)) == canonical_labels(gg.astype(np.int64))) >= 0.999
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="oracle/_ref not present")
+def test_live_reference_unbind_restart(tmp_path):
+    """-unbind <name>: restart from a .grp (FoF catalogue of a -nu run), centre-of-mass fallback."""
+    snap = synth.make_box(1 << 14, seed=12, kind="dark")
+    f = str(tmp_path / "in.std")
+    synth.write_std(snap, f)
+    refdump.run_ref(f, snap["ref_args"] + ["-nu"], str(tmp_path / "fof"))
+    os.remove(str(tmp_path / "fof.gtp"))  # force the centre-of-mass branch (kd.c:1160-1193)
+    unb = ["-std", "-tau", repr(snap["flags"]["tau"]), "-m", "8", "-H", "2.8944", "-p", "1", "-unbind",
+           str(tmp_path / "fof")]
+    out_ref, _ = refdump.run_ref(f, unb, str(tmp_path / "ref"))
+    out = run_skid(f, unb, str(tmp_path / "gpu"))
+    a, b = refdump.parse_log(out_ref), refdump.parse_log(out)
+    assert a["nGroupBefore"] == b["nGroupBefore"]
+    assert abs(a["nGroup"] - b["nGroup"]) <= 1
+    gr, gg = tipsy.read_array(str(tmp_path / "ref.grp")), tipsy.read_array(str(tmp_path / "gpu.grp"))
+    assert np.mean(canonical_labels(gr.astype(np.int64)) == canonical_labels(gg.astype(np.int64))) >= 0.999
