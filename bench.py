@@ -7,9 +7,11 @@ density + move + group + unbind, at 2^24).
 A "step" is one pass of the whole hot path (tree + kNN density, move-to-convergence, FoF, micro
 steps, centres, unbinding, too-small removal) over one synthetic snapshot.  Workload at N=1:
 BASELINE.json configs[2] - synthetic gas+dark box, 2^24 particles, moving both species (-gd),
-Lambda cosmology, unbinding on.  N>1 (torchrun, one rank per GPU): every rank
-groups its own snapshot of the same configuration (independent snapshots; no data-path collective;
-weak scaling) - see DESIGN.md "multi-GPU".
+Lambda cosmology, unbinding on.  N>1 (torchrun, one rank per GPU), weak
+scaling: ONE snapshot of N x 2^24 particles (N=8: the 2^27 box of configs[3]) sharded as the
+north_star says - particles, trees and scatterers replicated, kNN queries / movers / groups
+sharded, NCCL only for the small agreement points (skid_b200/parallel.py).
+`--mode replicas` instead runs N independent 2^24 snapshots with no collective at all.
 
 value     = particles / device time of the K timed steps with the snapshot already in HBM
             (CUDA events on the context's stream, max over ranks).
@@ -112,6 +114,7 @@ def main():
     ap.add_argument("--kind", default="gasdark", choices=["dark", "gasdark", "massive"])
     ap.add_argument("--cpu-log2n", type=int, default=17, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"], help="multi-GPU layout (N>1)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -158,21 +161,65 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n = 1 << a.log2n
-    snap = synth.make_box(n, seed=7 + rank, kind=a.kind)
-    fl = snap["flags"]
-    p = snap["pinit"]
-    # pinned host AoS (e2e leg) and device SoA (device-resident leg)
-    pin = torch.empty(n * PINIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    shard = world > 1 and a.mode == "shard"
+    n = (1 << a.log2n) * (world if shard else 1)
+    dev0 = torch.device("cuda", local)
+    if shard:
+        # one snapshot for everybody: rank 0 generates, NCCL broadcasts the SoA columns
+        from skid_b200 import parallel
+        meta = torch.zeros(4, dtype=torch.int64, device=dev0)
+        if rank == 0:
+            snap = synth.make_box(n, seed=7, kind=a.kind)
+            meta[:] = torch.tensor([snap["nGas"], snap["nDark"], snap["nStar"], n])
+        dist.broadcast(meta, 0)
+        nGas, nDark, nStar = int(meta[0]), int(meta[1]), int(meta[2])
+        dev = []
+        for k in range(9):
+            if rank == 0:
+                p = snap["pinit"]
+                col = (p["r"][:, k] if k < 3 else p["v"][:, k - 3] if k < 6 else p[("fMass", "fSoft", "fTemp")[k - 6]])
+                t = torch.from_numpy(np.ascontiguousarray(col)).to(dev0)
+            else:
+                t = torch.empty(n, dtype=torch.float32, device=dev0)
+            dist.broadcast(t, 0)
+            dev.append(t)
+        fl = synth.make_box(1024, seed=7, kind=a.kind)["flags"]
+        fl["tau"] = float(np.float32(0.0288 * n ** (-1.0 / 3.0)))
+        p = np.zeros(n, PINIT_DTYPE)
+        for k in range(9):
+            h = dev[k].cpu().numpy()
+            if k < 3:
+                p["r"][:, k] = h
+            elif k < 6:
+                p["v"][:, k - 3] = h
+            else:
+                p[("fMass", "fSoft", "fTemp")[k - 6]] = h
+        p["iOrder"] = np.arange(n, dtype=np.int32)
+        snap = dict(pinit=p, nGas=nGas, nDark=nDark, nStar=nStar, flags=fl)
+    else:
+        snap = synth.make_box(n, seed=7 + rank, kind=a.kind)
+        fl = snap["flags"]
+        p = snap["pinit"]
+        cols = [p["r"][:, 0], p["r"][:, 1], p["r"][:, 2], p["v"][:, 0], p["v"][:, 1], p["v"][:, 2], p["fMass"],
+                p["fSoft"], p["fTemp"]]
+        dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for c in cols]
+    # pinned host AoS (e2e leg)
+    try:
+        pin = torch.empty(n * PINIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    except Exception:
+        pin = torch.empty(n * PINIT_DTYPE.itemsize, dtype=torch.uint8)
     host_aos = pin.numpy().view(PINIT_DTYPE)
     host_aos[:] = p
-    cols = [p["r"][:, 0], p["r"][:, 1], p["r"][:, 2], p["v"][:, 0], p["v"][:, 1], p["v"][:, 2], p["fMass"], p["fSoft"],
-            p["fTemp"]]
-    dev = [torch.from_numpy(np.ascontiguousarray(c)).cuda() for c in cols]
+    del p
     torch.cuda.synchronize()
 
     per = (fl["period"],) * 3
     sk = api.SkidGPU(per, (0.0, 0.0, 0.0), bPeriodic=True, device=local)
+    reducer = None
+    if shard:
+        sk.set_shard(rank, world)
+        reducer = parallel.Reducer(dist, dev0, sk.stream())
+        sk.set_reduce_cb(reducer.cb)
     tau = float(np.float32(fl["tau"]))
     fCvg = float(np.float32(0.5 * tau))
     fScoop = float(np.float32(2.0 * tau))
@@ -183,6 +230,9 @@ def main():
     fCosmo = a32 * api.csmExp2Hub(a32, f32(fl["H0"]), f32(fl.get("Omega0", 1.0)), f32(fl.get("Lambda", 0.0)))
 
     def one_pass(host):
+        if shard:
+            return parallel.run_skid_sharded(sk, reducer, host_aos, snap["nGas"], snap["nDark"], snap["nStar"], fl,
+                                             rank, world, host=host, dev_ptrs=[t.data_ptr() for t in dev])
         sk.log = []
         if host:
             sk.set_particles(host_aos, snap["nGas"], snap["nDark"], snap["nStar"])
@@ -228,9 +278,14 @@ def main():
         stats["nMove"] = sk.nMove
         stats["d2h"] = grp.nbytes + cat.nbytes
         if dist is not None:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            t = torch.tensor([ms, float(stats["mover_steps"]), stats["move_kernel_ms"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+            tm = t[2:3].clone()
+            dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)   # mover-steps of all shards
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)        # slowest shard's kernel time
+            ms = float(t[0].item())
+            stats["mover_steps"] = float(t[1].item())
+            stats["move_kernel_ms"] = float(tm.item())
         return ms, stats
 
     W = max(a.warmup, 3)
@@ -242,7 +297,7 @@ def main():
     timed(True, 1)                        # warm the host path (pinned staging, pool growth)
     ms_e2e, st_e = timed(True, a.steps)
 
-    total_particles = n * world
+    total_particles = n if shard else n * world
     value = total_particles * a.steps / (ms_dev * 1e-3)
     e2e_value = total_particles * a.steps / (ms_e2e * 1e-3)
     peak, peak_src = load_peaks()
@@ -257,8 +312,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "particles_per_gpu": n, "nSmooth": fl["nSmooth"], "tau": tau,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent snapshots, one per GPU",
+        "config": {"workload": workload, "particles_per_gpu": 1 << a.log2n, "nSmooth": fl["nSmooth"], "tau": tau,
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"one {n}-particle snapshot sharded over {world} GPUs: replicated scatterers/trees, sharded "
+                       f"kNN queries, movers and groups; NCCL all-reduce at {reducer.calls // max(1, (W + a.steps + 1 + a.steps))} agreement "
+                       f"points per step" if shard else f"{world} independent snapshots, one per GPU"),
                    "l2": "inputs (604 MB SoA at 2^24) larger than the 126 MB L2; no explicit flush",
                    "movers": st["nMove"], "groups_before_unbind": st["groups_before"], "groups": st["groups"],
                    "unbound": st["unbound"]},
@@ -276,6 +334,9 @@ def main():
                      "avg_launch_ms": st["move_kernel_ms"] / max(st["move_launches"], 1),
                      "share_of_step": st["move_kernel_ms"] / ms_dev},
     }
+    if shard:
+        out["config"]["particles_total"] = n
+        out["config"]["nccl_bytes_per_step"] = reducer.bytes // max(1, (W + a.steps + 1 + a.steps))
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             v, info = run_reference_sample(a.kind, a.cpu_log2n, seed=7)

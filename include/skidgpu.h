@@ -88,6 +88,22 @@ int skidgpu_set_particles_dev(skidgpu_ctx *ctx, const float *dx, const float *dy
 /* kdSetSoft (kd.c:103-110, main.c:464): override every softening. */
 int skidgpu_set_soft(skidgpu_ctx *ctx, float fEps);
 
+/* Multi-GPU exchange hook.  When nranks > 1 the library calls `cb` at the few points where ranks
+ * must agree: the buffer is DEVICE memory of this context, the call is made after all
+ * producing work has been enqueued on the context's stream (skidgpu_stream) and the reduced result
+ * must be visible to work enqueued on that stream afterwards (e.g. an NCCL all-reduce issued on it).
+ * dtype: 0 int32, 1 uint8, 2 float32, 3 float64.  op: 0 min, 1 max, 2 sum.  Return 0 on success.
+ * Call sites: sum of fBall2/density partials (sharded kNN queries), max of the step-0 "touched"
+ * flags, min of fScatDens every step, sum of the active-mover count every 5 steps, min of labels and
+ * sum of catalogue rows / unbound count after the sharded unbinding. */
+typedef int (*skidgpu_reduce_cb)(void *user, void *dev, long long count, int dtype, int op);
+int skidgpu_set_reduce_cb(skidgpu_ctx *ctx, skidgpu_reduce_cb cb, void *user);
+
+/* Device arrays x,y,z (nMove floats each) of the current mover positions and the [lo,hi) range of
+ * movers this shard owns; the caller all-gathers the owned ranges before skidgpu_fof and
+ * skidgpu_centers (positions of movers owned by other ranks are stale otherwise). */
+int skidgpu_mover_arrays(skidgpu_ctx *ctx, float **dx, float **dy, float **dz, int *nMove, int *lo, int *hi);
+
 /* kdScatterActive + kdBuildTree + smInit + smDensityInit (main.c:374-378):
  * tree over the scatter-active species, exact periodic k-nearest (k = nSmooth, self
  * included), fBall2 = k-th distance^2 (bitwise as the reference), symmetric

@@ -32,7 +32,7 @@ EXPORTS = [
     "skidgpu_get_neighbors", "skidgpu_move", "skidgpu_keep_step0", "skidgpu_get_step0", "skidgpu_fof",
     "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_moved_dev", "skidgpu_centers", "skidgpu_set_groups",
     "skidgpu_unbind", "skidgpu_stage_ms", "skidgpu_counter", "skidgpu_debug_sort", "skidgpu_debug_scan",
-    "skidgpu_kernel_ms", "skidgpu_stream",
+    "skidgpu_kernel_ms", "skidgpu_stream", "skidgpu_set_reduce_cb", "skidgpu_mover_arrays",
 ]
 
 
@@ -76,6 +76,8 @@ def load_library():
     lib.skidgpu_kernel_ms.restype = d
     lib.skidgpu_stream.argtypes = [vp]
     lib.skidgpu_stream.restype = vp
+    lib.skidgpu_set_reduce_cb.argtypes = [vp, vp, vp]
+    lib.skidgpu_mover_arrays.argtypes = [vp, P(vp), P(vp), P(vp), P(i), P(i), P(i)]
     lib.skidgpu_debug_sort.argtypes = [vp, vp, vp, C.c_longlong, i]
     lib.skidgpu_debug_scan.argtypes = [vp, vp, vp, C.c_longlong]
     _lib = lib
@@ -145,6 +147,18 @@ class SkidGPU:
 
     def set_shard(self, rank, nranks):
         self._ck(self.lib.skidgpu_set_shard(self.h, rank, nranks))
+
+    def set_reduce_cb(self, cfunc):
+        """cfunc: a parallel.REDUCE_CB instance (kept alive by the caller) or None."""
+        self._reduce_cb = cfunc
+        self._ck(self.lib.skidgpu_set_reduce_cb(self.h, C.cast(cfunc, C.c_void_p) if cfunc else None, None))
+
+    def mover_arrays(self):
+        px, py, pz = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nm, lo, hi = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._ck(self.lib.skidgpu_mover_arrays(self.h, C.byref(px), C.byref(py), C.byref(pz), C.byref(nm),
+                                               C.byref(lo), C.byref(hi)))
+        return px.value, py.value, pz.value, nm.value, lo.value, hi.value
 
     def kdSetSoft(self, fEps):
         self._ck(self.lib.skidgpu_set_soft(self.h, fEps))

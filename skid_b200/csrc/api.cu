@@ -360,6 +360,27 @@ extern "C" double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage)
 	return ctx->stage_ms[stage];
 }
 
+extern "C" int skidgpu_set_reduce_cb(skidgpu_ctx *ctx, skidgpu_reduce_cb cb, void *user)
+{
+	API_BEGIN(ctx)
+	ctx->reduceCb = cb;
+	ctx->reduceUser = user;
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_mover_arrays(skidgpu_ctx *ctx, float **dx, float **dy, float **dz, int *nMove, int *lo, int *hi)
+{
+	API_BEGIN(ctx)
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (dx) *dx = ctx->mx.p;
+	if (dy) *dy = ctx->my.p;
+	if (dz) *dz = ctx->mz.p;
+	if (nMove) *nMove = ctx->nMove;
+	if (lo) *lo = ctx->shardLo;
+	if (hi) *hi = ctx->shardHi;
+	API_END(ctx)
+}
+
 extern "C" double skidgpu_kernel_ms(skidgpu_ctx *ctx, int which, int *nLaunches)
 {
 	if (!ctx || which < 0 || which > 1) return -1.0;

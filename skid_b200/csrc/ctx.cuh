@@ -10,6 +10,8 @@ struct skidgpu_ctx {
 	float L[3], C[3];
 	int bPeriodic = 0, bDiag = 0;
 	int rank = 0, nranks = 1;
+	skidgpu_reduce_cb reduceCb = nullptr;
+	void *reduceUser = nullptr;
 
 	// ---- particles, SoA by iOrder (file order: gas, dark, star; kd.c:113-119)
 	int n = 0, nGas = 0, nDark = 0, nStar = 0, inType = 0;
@@ -109,6 +111,21 @@ struct KernelTimer {
 		open = false;
 	}
 };
+
+// multi-GPU agreement point (no-op on one rank)
+static inline void sk_reduce(skidgpu_ctx &c, void *dev, long long count, int dtype, int op)
+{
+	if (c.nranks <= 1) return;
+	if (!c.reduceCb) throw SkidError("nranks > 1 but no reduce callback set (skidgpu_set_reduce_cb)");
+	if (c.reduceCb(c.reduceUser, dev, count, dtype, op) != 0) throw SkidError("reduce callback failed");
+}
+#define SK_I32 0
+#define SK_U8 1
+#define SK_F32 2
+#define SK_F64 3
+#define SK_MIN 0
+#define SK_MAX 1
+#define SK_SUM 2
 
 // stage entry points (each in its own .cu)
 void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, int *nExtraScat);

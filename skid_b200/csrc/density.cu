@@ -119,6 +119,7 @@ struct KnnArgs {
 	const float4 *pos4;
 	const int *iord;
 	int n, k;
+	int qLo, qHi; // this rank's range of queries (sorted order); all of [0,n) on one GPU
 	float L[3], hL[3];
 	float boxLo[3], boxHi[3]; // the periodic box (centre -+ L/2); +-FLT_MAX when not periodic
 	float *ball2;
@@ -222,8 +223,8 @@ __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 	__shared__ uint64_t s_buf[KNN_WARPS][64];
 	__shared__ float s_dist[KNN_WARPS][SK_MAXLEV][32];
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int qi = blockIdx.x * KNN_WARPS + w;
-	if (qi >= a.n) return;
+	const int qi = a.qLo + blockIdx.x * KNN_WARPS + w;
+	if (qi >= a.qHi) return;
 	const int n = a.n, k = a.k;
 	const float4 qp = a.pos4[qi];
 	KnnQuery q;
@@ -503,13 +504,21 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	ka.nbr = c.keepNbr ? c.nbr.p : nullptr;
 	ka.nbrD2 = c.keepNbr ? c.nbrD2.p : nullptr;
 	CK(cudaMemsetAsync(ka.rho64, 0, sizeof(double) * m, s));
+	CK(cudaMemsetAsync(ka.ball2, 0, sizeof(float) * m, s));
+	// multi-GPU: queries are sharded by contiguous Morton ranges; fBall2 (one writer per entry) and the
+	// f64 density partials are summed across ranks, so every rank ends with identical arrays
+	ka.qLo = (int)((long long)m * c.rank / c.nranks);
+	ka.qHi = (int)((long long)m * (c.rank + 1) / c.nranks);
 	KernelTimer kt(c, 1);
 	c.kernel_ms[1] = 0;
 	c.kernel_launches[1] = 0;
 	kt.start();
-	SK_LAUNCH(k_knn_density, (unsigned)ceil_div(m, KNN_WARPS), KNN_WARPS * 32, 0, s, ka);
+	if (ka.qHi > ka.qLo)
+		SK_LAUNCH(k_knn_density, (unsigned)ceil_div(ka.qHi - ka.qLo, KNN_WARPS), KNN_WARPS * 32, 0, s, ka);
 	kt.stop(1);
-	c.nQueries += m;
+	sk_reduce(c, ka.ball2, m, SK_F32, SK_SUM);
+	sk_reduce(c, ka.rho64, m, SK_F64, SK_SUM);
+	c.nQueries += ka.qHi - ka.qLo;
 	float *rhoA = c.rhoA.alloc(m);
 	SK_LAUNCH(k_density_finish, (unsigned)ceil_div(m, 256), 256, 0, s, m, iordA, ka.rho64, ka.ball2, rhoA, c.rho.p,
 	          c.ball2.p);

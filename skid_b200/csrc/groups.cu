@@ -474,6 +474,7 @@ struct UnbArgs {
 	int iSoftType, bNoUnbind, nMaxMembers, bSubPot;
 	unsigned int *nUnbound;
 	unsigned long long *nPairs;
+	int rank, nranks;
 };
 
 constexpr int UNB_T = 256;
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const int beg = a.gStart[g];
 	int n = a.gStart[g + 1] - beg;
-	if (n >= a.nMaxMembers || n <= 0) return;
+	if (n >= a.nMaxMembers || n <= 0 || (g % a.nranks) != a.rank) return;
 	float4 *qr = a.qr + beg, *qv = a.qv + beg;
 	int *qord = a.qord + beg;
 	double *pot = a.pot + beg;
@@ -720,12 +721,43 @@ __global__ void __launch_bounds__(256)
 	atomicMax((unsigned int *)&cat[g].fRadius, __float_as_uint(fr));
 }
 
-__global__ void __launch_bounds__(256) k_tiles_per_group(int nGroup, const int *gN, int nMax, uint32_t *tiles)
+// multi-GPU: group g is unbound by rank g % nranks; everybody else contributes nothing to the merge
+__global__ void __launch_bounds__(256) k_tiles_per_group(int nGroup, const int *gN, int nMax, uint32_t *tiles,
+                                                         int rank, int nranks)
 {
 	int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= nGroup) return;
 	int n = gN[g];
-	tiles[g] = (g == 0 || n >= nMax) ? 0u : (uint32_t)((n + POT_T - 1) / POT_T);
+	tiles[g] = (g == 0 || n >= nMax || (g % nranks) != rank) ? 0u : (uint32_t)((n + POT_T - 1) / POT_T);
+}
+
+// catalogue rows that unbinding changes, packed for the cross-rank sum: owner's values, zeros elsewhere
+__global__ void __launch_bounds__(256) k_cat_pack(int nGroup, const skidgpu_pgroup *cat, const int *gN, int rank,
+                                                  int nranks, float *f)
+{
+	int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= nGroup) return;
+	float *o = f + (size_t)g * 8;
+	bool own = g > 0 && (g % nranks) == rank;
+	o[0] = own ? cat[g].fMass : 0.0f;
+	for (int j = 0; j < 3; ++j) {
+		o[1 + j] = own ? cat[g].vcm[j] : 0.0f;
+		o[4 + j] = own ? cat[g].rBound[j] : 0.0f;
+	}
+	o[7] = own ? (float)gN[g] : 0.0f;
+}
+__global__ void __launch_bounds__(256) k_cat_unpack(int nGroup, skidgpu_pgroup *cat, int *gN, const float *f)
+{
+	int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= nGroup || g == 0) return;
+	const float *o = f + (size_t)g * 8;
+	cat[g].fMass = o[0];
+	for (int j = 0; j < 3; ++j) {
+		cat[g].vcm[j] = o[1 + j];
+		cat[g].rBound[j] = o[4 + j];
+	}
+	gN[g] = (int)(o[7] + 0.5f);
+	cat[g].nMembers = gN[g];
 }
 
 __global__ void __launch_bounds__(256) k_copy_counts(int nGroup, const int *gN, uint32_t *out)
@@ -904,7 +936,8 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			// ---- potentials
 			tiles.alloc(G + 2);
 			tileStart.alloc(G + 2);
-			SK_LAUNCH(k_tiles_per_group, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, nMaxMembers, tiles.p);
+			SK_LAUNCH(k_tiles_per_group, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, nMaxMembers, tiles.p, c.rank,
+			          c.nranks);
 			exclusive_scan_u32(tiles.p, tileStart.p, G, c.ws, s);
 			uint32_t nTiles = 0;
 			CK(cudaMemcpyAsync(&nTiles, tileStart.p + G, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -951,7 +984,19 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			ua.bSubPot = (c.inType == SKIDGPU_DARK || c.inType == SKIDGPU_STAR) ? 1 : 0; // kd.c:1441
 			ua.nUnbound = dCnt.p;
 			ua.nPairs = nullptr;
+			ua.rank = c.rank;
+			ua.nranks = c.nranks;
 			SK_LAUNCH(k_unbind, (unsigned)(G - 1), UNB_T, 0, s, ua);
+			if (c.nranks > 1) { // merge the shards: labels (owner wrote 0 for unbound members), rows, count
+				DevBuf<float> pack;
+				pack.alloc((size_t)G * 8);
+				sk_reduce(c, c.gid.p, n, SK_I32, SK_MIN);
+				SK_LAUNCH(k_cat_pack, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gCat.p, c.gN.p, c.rank, c.nranks, pack.p);
+				sk_reduce(c, pack.p, (long long)G * 8, SK_F32, SK_SUM);
+				SK_LAUNCH(k_cat_unpack, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gCat.p, c.gN.p, pack.p);
+				sk_reduce(c, dCnt.p, 1, SK_I32, SK_SUM);
+				CK(cudaStreamSynchronize(s));
+			}
 			CK(cudaMemcpyAsync(&hUnbound, dCnt.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
 			CK(cudaStreamSynchronize(s));
 		}

@@ -112,6 +112,7 @@ struct StepArgs {
 	// candidate lists (k_move_list): per mover LIST_CAP scatterer indices, list origin, margin,
 	// count (-1 = no valid list), and the smallest containing ball radius seen at the last walk
 	uint32_t *list;
+	uint32_t listBase; // first mover id of this shard
 	float *lx0, *ly0, *lz0, *ldelta, *lhmin;
 	int *lcnt;
 	int walkAlways; // debug (SKIDGPU_LIST_WALK_ALWAYS=1): never use the lists
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_move_list(const StepArgs a)
 	const float T = __uint_as_float(a.dT[0]);
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
 	float rmin = 3.0e38f;
-	uint32_t *list = a.list + (size_t)id * LIST_CAP;
+	uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP; // lists exist for this shard's movers only
 
 	// smAccDensity (smooth1.c:447-459) for one hit.  Same float32 operations as the reference
 	// (r2 = d2*ih2, rs = sqrt(r2), rs *= fNorm, a += dx*rs, all round-to-nearest, no FMA on the sums);
@@ -508,6 +509,7 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	}
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
 	sa.list = c.mList.p;
+	sa.listBase = (uint32_t)c.shardLo;
 	sa.lx0 = c.lx0.p;
 	sa.ly0 = c.ly0.p;
 	sa.lz0 = c.lz0.p;
@@ -570,6 +572,7 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 			SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
 		c.moverSteps += c.nActive;
 	}
+	if (!bNoPrune) sk_reduce(c, c.dT.p + 1, 1, SK_I32, SK_MIN); // fScatDens over all ranks' movers (+inf bits = none)
 	SK_LAUNCH(k_update_T, 1, 1, 0, c.stream, c.dT.p, bNoPrune);
 	return launched;
 }
@@ -625,7 +628,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.ldelta.alloc(m);
 		c.lhmin.alloc(m);
 		c.lcnt.alloc(m);
-		if (use_list_kernel()) c.mList.alloc((size_t)m * LIST_CAP);
+		if (use_list_kernel()) c.mList.alloc((size_t)(c.shardHi - c.shardLo > 0 ? c.shardHi - c.shardLo : 1) * LIST_CAP);
 		SK_LAUNCH(k_init_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeM.perm.p, fileIdx, c.x.p, c.y.p,
 		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p, c.ball2.p, c.lhmin.p, c.lcnt.p, c.listInitFactor);
 		c.actList.alloc(m);
@@ -657,7 +660,8 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.kernel_launches[0] = 0;
 	kt.start();
 	kt.stop(one_step(c, sa, bNoPrune));
-	if (bInitial && c.nEnt > 0 && c.nranks == 1)
+	if (bInitial && c.nEnt > 0) sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
+	if (bInitial && c.nEnt > 0)
 		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p);
 	sa.touched = nullptr;
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
@@ -667,33 +671,48 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		          c.iordA.p, c.dT.p, c.aliveByOrd.p);
 	}
 	int nScat = count_scatterers(c);
-	if (cb) cb(user, 0, 0, nActiveLog, nScat);
+	if (cb) cb(user, 0, 0, c.nranks > 1 ? m : nActiveLog, nScat);
 
 	// ---- main flow loop (main.c:408-419)
 	const float hx = (float)(0.5 * (double)c.L[0]), hy = (float)(0.5 * (double)c.L[1]),
 	            hz = (float)(0.5 * (double)c.L[2]);
 	const float fCvg2 = fCvg * fCvg;
 	int nIttr = 1;
-	while (c.nActive) {
+	// all ranks iterate until NO rank has an active mover (the per-step fScatDens is a global minimum)
+	auto global_active = [&](int local) -> long long {
+		if (c.nranks <= 1) return local;
+		uint32_t *d = c.dCount.alloc(4);
+		uint32_t h = (uint32_t)local;
+		CK(cudaMemcpyAsync(d + 1, &h, sizeof h, cudaMemcpyHostToDevice, s));
+		sk_reduce(c, d + 1, 1, SK_I32, SK_SUM);
+		CK(cudaMemcpyAsync(&h, d + 1, sizeof h, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		return (long long)h;
+	};
+	long long nGlobal = global_active(c.nActive);
+	while (nGlobal) {
 		int nl = 0;
 		kt.start();
 		for (int i = 0; i < 5; ++i) nl += one_step(c, sa, bNoPrune);
 		kt.stop(nl);
 		// kdPruneInactive
-		uint32_t *pf = c.flags.alloc(c.nActive);
-		uint32_t *ps = c.scan.alloc((size_t)c.nActive + 64);
-		SK_LAUNCH(k_prune_flags, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
-		          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, hx, hy, hz, fCvg2, pf);
-		exclusive_scan_u32(pf, ps, c.nActive, c.ws, s);
-		SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, ps,
-		          c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p);
 		uint32_t na = 0;
-		CK(cudaMemcpyAsync(&na, ps + c.nActive, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		if (c.nActive > 0) {
+			uint32_t *pf = c.flags.alloc(c.nActive);
+			uint32_t *ps = c.scan.alloc((size_t)c.nActive + 64);
+			SK_LAUNCH(k_prune_flags, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
+			          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, hx, hy, hz, fCvg2, pf);
+			exclusive_scan_u32(pf, ps, c.nActive, c.ws, s);
+			SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, ps,
+			          c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p);
+			CK(cudaMemcpyAsync(&na, ps + c.nActive, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+		}
 		nScat = count_scatterers(c); // synchronises
 		c.nActive = (int)na;
 		std::swap(c.actList.p, c.actList2.p);
 		std::swap(c.actList.cap, c.actList2.cap);
-		if (cb) cb(user, 0, nIttr, c.nActive, nScat);
+		nGlobal = global_active(c.nActive);
+		if (cb) cb(user, 0, nIttr, (int)nGlobal, nScat);
 		++nIttr;
 	}
 	if (nIttrOut) *nIttrOut = nIttr;
