@@ -43,6 +43,7 @@ struct skidgpu_ctx {
 	DevBuf<uint32_t> entSrcU; // unsorted: sorted-A index | 0x80000000 for a replica
 	DevBuf<float4> entPos;   // sorted (x,y,z,ball2)
 	DevBuf<float4> entNR;    // sorted (4/fBall2, fNorm, rhoEff, 0): rhoEff = 0 once cut at step 0
+	DevBuf<float4> entRec;   // sorted, interleaved copy: rec[2e] = entPos[e], rec[2e+1] = entNR[e]
 	DevBuf<uint32_t> entSrc;
 	DevBuf<uint8_t> entTouched;
 	BoxTree treeE;
@@ -57,6 +58,7 @@ struct skidgpu_ctx {
 	DevBuf<float> lx0, ly0, lz0, ldelta, lhmin;
 	DevBuf<int> lcnt;
 	float listInitFactor = 0.3f;
+	DevBuf<uint32_t> mQueue; // movers that refresh their list this step
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step

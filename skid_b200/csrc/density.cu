@@ -414,14 +414,18 @@ __global__ void __launch_bounds__(256)
 
 __global__ void __launch_bounds__(256)
     k_gather_entities(int m, const uint32_t *perm, const float4 *posU, const float4 *nrU, const uint32_t *srcU,
-                      const float *inflU, float4 *pos, float4 *nr, uint32_t *src, float *infl, float *rho)
+                      const float *inflU, float4 *pos, float4 *nr, uint32_t *src, float *infl, float *rho,
+                      float4 *rec)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m) return;
 	uint32_t j = perm[i];
-	pos[i] = posU[j];
+	float4 pp = posU[j];
+	pos[i] = pp;
 	float4 v = nrU[j];
 	nr[i] = v;
+	rec[2 * (size_t)i] = pp;
+	rec[2 * (size_t)i + 1] = v;
 	src[i] = srcU[j];
 	infl[i] = inflU[j];
 	rho[i] = v.z;
@@ -568,8 +572,9 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	uint32_t *esrc = c.entSrc.alloc(ne);
 	float *inflS = c.tmpx.alloc(ne);
 	float *rhoS = c.eRhoSorted.alloc(ne);
+	float4 *erec = c.entRec.alloc(2 * ((size_t)ne + 64));
 	SK_LAUNCH(k_gather_entities, (unsigned)ceil_div(ne, 256), 256, 0, s, ne, c.treeE.perm.p, posU, nrU, srcU, einfl, ep,
-	          enr, esrc, inflS, rhoS);
+	          enr, esrc, inflS, rhoS, erec);
 	// pad the sorted scatterer arrays to whole leaves with dummies that can never be hit (fBall2 = -1)
 	SK_LAUNCH(k_pad_entities, 1, 64, 0, s, ne, ep, enr);
 	tree_build_boxes(c.treeE, ep, inflS, rhoS, ne, s, 32, 32);

@@ -17,6 +17,7 @@
 
 #define T_NONE 0x7f800000u // +inf bits: "no entity was hit this step"
 
+
 // CutCriterion (kd.c:555-597)
 __global__ void __launch_bounds__(256)
     k_mover_flags(int n, int nGas, int nDark, int inType, int bGasAndDark, int bGasOnly, const float *rho,
@@ -99,6 +100,7 @@ struct StepArgs {
 	TreeView tv;
 	const float4 *entPos; // (x,y,z,fBall2)
 	const float4 *entNR;  // (4/fBall2, fNorm, rhoEff, 0)
+	const float4 *entRec; // the two interleaved: rec[2e] = entPos[e], rec[2e+1] = entNR[e] (list path gathers)
 	uint8_t *touched;     // nullable: set for entities with >= 1 hit (step 0, initial cut)
 	float *mx, *my, *mz;
 	const uint32_t *act;
@@ -118,6 +120,8 @@ struct StepArgs {
 	int walkAlways; // debug (SKIDGPU_LIST_WALK_ALWAYS=1): never use the lists
 	float polShrink, polGrow; // margin feedback (see k_move_list)
 	int polGrowMax;
+	uint32_t *queue;      // movers whose list must be refreshed this step
+	uint32_t *queueCount; // = dT + 2, reset by k_update_T
 };
 
 constexpr int STEP_WARPS = 8;
@@ -240,159 +244,60 @@ __device__ __forceinline__ void move_one(const StepArgs &a, uint32_t id, float x
 	a.mz[id] = r[2];
 }
 
-// Default kernel: warp-per-mover walk + per-mover candidate lists ("Verlet lists").
+// smAccDensity (smooth1.c:447-459) for one hit.  Same float32 operations as the reference
+// (r2 = d2*ih2, rs = sqrt(r2), rs *= fNorm, a += dx*rs, all round-to-nearest, no FMA on the sums);
+// the spline factor, which the reference evaluates in double and rounds to float, is formed with
+// one FMA (inner branch, a single rounding of the exact value) or with a float division plus its
+// exact-remainder correction (outer branch), i.e. to float accuracy without double arithmetic.
+#define ACC_HIT(dx, dy, dz, d2, q)                                                                     \
+{                                                                                              \
+	const float r2_ = __fmul_rn((d2), (q).x);                                              \
+	const float rs_ = __fsqrt_rn(r2_);                                                     \
+	float g_;                                                                              \
+	if (r2_ < 1.0f) g_ = fmaf(2.25f, rs_, -3.0f);                                          \
+	else {                                                                                 \
+		const float t_ = __fdiv_rn(-3.0f, rs_);                                        \
+		const float c_ = __fdividef(fmaf(-t_, rs_, -3.0f), rs_);                       \
+		g_ = fmaf(-0.75f, rs_, 3.0f + t_) + c_;                                        \
+	}                                                                                      \
+	g_ = __fmul_rn(g_, (q).y);                                                             \
+	ax = __fadd_rn(ax, __fmul_rn((dx), g_));                                               \
+	ay = __fadd_rn(ay, __fmul_rn((dy), g_));                                               \
+	az = __fadd_rn(az, __fmul_rn((dz), g_));                                               \
+	rmin = fminf(rmin, (q).z);                                                             \
+}
+
+
+// Default kernels: per-mover candidate lists ("Verlet lists").
 //
 // ncu on the v1 kernel above (profiles/r01_v1_move_*): issue-bound, ~3600 warp instructions per
 // mover-step, of which ~85 % are tree bookkeeping and misses (1500 scatterers tested for 85 hits).
 // A mover travels exactly fStep (= tau/4) per step while the balls that contain it have radii of
-// many tau, so the set of scatterers that CAN contain it changes slowly.  Each mover therefore keeps
-// the list of scatterers e with |x_e - x0| < h_e + delta found by one tree walk at x0; as long as the
-// mover stays within delta of x0 every scatterer that contains it is in the list (triangle
-// inequality), and a step is just: read the list (1 KB, coalesced), gather those scatterers, run the
-// SAME float32 hit test, accumulate.  When the mover has drifted past delta (or wrapped around the
-// box) the warp walks the tree again, evaluating this step's gradient and emitting the new list in
-// the same pass.  The hit set, the hit test and the pruning rule are exactly those of v1.
+// many tau, so the set of scatterers that CAN contain it changes slowly.  Each mover keeps the list
+// of scatterers e with |x_e - x0| < h_e + delta collected by one tree walk at x0; while it stays
+// within delta of x0 every scatterer that contains it is in the list (triangle inequality), and a
+// step only reads the list, gathers those scatterers and runs the SAME float32 hit test.
+//
+//  * k_list_eval   (every step, one warp per active mover, small register footprint -> full
+//                   occupancy; it is latency bound): movers with a valid list take their step;
+//                   the others are appended to a refresh queue.
+//  * k_list_refresh(every step, one warp per queued mover): walks the tree, evaluating this step
+//                   and emitting the new list in the same pass.  Leaf buckets are fetched two at a
+//                   time to keep more loads in flight.
+//
+// Splitting the two keeps warps that run ~10x longer out of the blocks of the short ones.  The margin
+// delta is feedback-controlled per mover (tools/sweep_policy.sh).  The hit set, the hit test and the
+// pruning rule are exactly those of v1 (verified against it and against the reference: same groups,
+// same Ittr trace).  A periodic wrap moves the mover by L, which fails the drift check by construction.
 constexpr int LIST_CAP = 384;
+constexpr int EVAL_WARPS = 4;
+constexpr int REFRESH_WARPS = 4;
 
-__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_list(const StepArgs a)
+// the end of every step for one mover: min density of the scatterers that hit it, optional copy of
+// the acceleration, kdMoveParticles
+__device__ __forceinline__ void finish_step(const StepArgs &a, uint32_t id, float x, float y, float z, float ax,
+                                            float ay, float az, float rmin, int lane)
 {
-	const int lane = threadIdx.x & 31;
-	const uint32_t lt = (1u << lane) - 1u;
-	const int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
-	if (wi >= a.nActive) return;
-	const uint32_t id = a.act[wi];
-	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
-	const float T = __uint_as_float(a.dT[0]);
-	float ax = 0.0f, ay = 0.0f, az = 0.0f;
-	float rmin = 3.0e38f;
-	uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP; // lists exist for this shard's movers only
-
-	// smAccDensity (smooth1.c:447-459) for one hit.  Same float32 operations as the reference
-	// (r2 = d2*ih2, rs = sqrt(r2), rs *= fNorm, a += dx*rs, all round-to-nearest, no FMA on the sums);
-	// the spline factor, which the reference evaluates in double and rounds to float, is formed with
-	// one FMA (inner branch, a single rounding of the exact value) or with a float division plus its
-	// exact-remainder correction (outer branch), i.e. to float accuracy without double arithmetic.
-#define ACC_HIT(dx, dy, dz, d2, q)                                                                     \
-	{                                                                                              \
-		const float r2_ = __fmul_rn((d2), (q).x);                                              \
-		const float rs_ = __fsqrt_rn(r2_);                                                     \
-		float g_;                                                                              \
-		if (r2_ < 1.0f) g_ = fmaf(2.25f, rs_, -3.0f);                                          \
-		else {                                                                                 \
-			const float t_ = __fdiv_rn(-3.0f, rs_);                                        \
-			const float c_ = __fdividef(fmaf(-t_, rs_, -3.0f), rs_);                       \
-			g_ = fmaf(-0.75f, rs_, 3.0f + t_) + c_;                                        \
-		}                                                                                      \
-		g_ = __fmul_rn(g_, (q).y);                                                             \
-		ax = __fadd_rn(ax, __fmul_rn((dx), g_));                                               \
-		ay = __fadd_rn(ay, __fmul_rn((dy), g_));                                               \
-		az = __fadd_rn(az, __fmul_rn((dz), g_));                                               \
-		rmin = fminf(rmin, (q).z);                                                             \
-	}
-
-	const int cnt0 = a.lcnt[id];
-	bool useList = false;
-	if (cnt0 >= 0 && !a.walkAlways) {
-		const float ox = x - a.lx0[id], oy = y - a.ly0[id], oz = z - a.lz0[id];
-		const float dl = a.ldelta[id];
-		useList = (ox * ox + oy * oy + oz * oz) * 1.0001f <= dl * dl;
-	}
-	if (useList) {
-		// ---- list path
-		for (int s0 = 0; s0 < cnt0; s0 += 32) {
-			const int s = s0 + lane;
-			if (s < cnt0) {
-				const uint32_t e = list[s];
-				const float4 p = a.entPos[e];
-				// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
-				const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
-				const float d2 = dist2_rn(dx, dy, dz);
-				if (d2 < p.w) {
-					const float4 q = a.entNR[e];
-					if (q.z >= T) ACC_HIT(dx, dy, dz, d2, q);
-				}
-			}
-		}
-	} else {
-		// ---- walk path: evaluate this step AND emit the candidate list for the next ones
-		const float delta = fminf(fmaxf(a.lhmin[id], 2.0f * a.fStep), 64.0f * a.fStep); // lhmin = margin to use
-		const float delta2 = delta * delta;
-		int nHit = 0;
-		int cnt = 0;
-		bool overflow = false;
-		int lev = a.tv.top - 1;
-		uint32_t node = 0, mymask = 0;
-		const float bx0 = x - delta, bx1 = x + delta, by0 = y - delta, by1 = y + delta, bz0 = z - delta, bz1 = z + delta;
-#define LIST_TEST_CHILDREN()                                                                           \
-	{                                                                                              \
-		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
-		float4 lo = bx[0], hi = bx[1];                                                         \
-		bool in_ = bx1 >= lo.x && bx0 <= hi.x && by1 >= lo.y && by0 <= hi.y && bz1 >= lo.z && bz0 <= hi.z && \
-		           lo.w >= T;                                                                  \
-		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
-		if (lane == lev) mymask = m_;                                                          \
-	}
-		LIST_TEST_CHILDREN();
-		while (true) {
-			uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
-			if (m == 0) {
-				++lev;
-				if (lev >= a.tv.top) break;
-				node >>= 5;
-				continue;
-			}
-			int c = __ffs(m) - 1;
-			m &= m - 1;
-			if (lane == lev) mymask = m;
-			uint32_t child = node * 32 + c;
-			if (lev > 0) {
-				--lev;
-				node = child;
-				LIST_TEST_CHILDREN();
-				continue;
-			}
-			const uint32_t e = child * 32 + lane; // arrays are padded with fBall2 = -1 dummies
-			const float4 p = a.entPos[e];
-			const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
-			const float d2 = dist2_rn(dx, dy, dz);
-			// candidate: can contain the mover while it stays within delta of here, i.e.
-			// d <= h + delta  <=>  u = d2 - h^2 - delta^2 <= 2 h delta  (no square root; 1e-4 slack)
-			const float u = d2 - p.w - delta2;
-			bool cand = p.w > 0.0f && (u <= 0.0f || u * u <= 4.0004f * p.w * delta2);
-			if (cand) {
-				const float4 q = a.entNR[e];
-				cand = q.z >= T; // dead scatterers never come back
-				if (cand && d2 < p.w) {
-					ACC_HIT(dx, dy, dz, d2, q);
-					++nHit;
-					if (a.touched) a.touched[e] = 1;
-				}
-			}
-			const uint32_t cm = __ballot_sync(SK_FULL, cand);
-			const int nc = __popc(cm);
-			if (cnt + nc <= LIST_CAP) {
-				if (cand) list[cnt + __popc(cm & lt)] = e;
-			} else overflow = true;
-			cnt += nc;
-		}
-#undef LIST_TEST_CHILDREN
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1) nHit += __shfl_xor_sync(SK_FULL, nHit, o);
-		if (lane == 0) {
-			a.lcnt[id] = overflow ? -1 : cnt;
-			a.lx0[id] = x;
-			a.ly0[id] = y;
-			a.lz0[id] = z;
-			a.ldelta[id] = delta;
-			// feedback on the margin: a walk costs ~15 list steps, so grow the margin while the list
-			// stays short (< 2.5 x the hits and well below the capacity), shrink it when it is long
-			float next = delta;
-			if (overflow || (float)cnt > a.polShrink * nHit + 32.0f) next = 0.6f * delta;
-			else if ((float)cnt < a.polGrow * nHit + 32.0f && cnt < a.polGrowMax) next = 1.5f * delta;
-			a.lhmin[id] = next;
-		}
-	}
-#undef ACC_HIT
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
 		ax += __shfl_xor_sync(SK_FULL, ax, o);
@@ -411,6 +316,152 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_move_list(const StepArgs a)
 	}
 }
 
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 16) k_list_eval(const StepArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const int wi = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
+	if (wi >= a.nActive) return;
+	const uint32_t id = a.act[wi];
+	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+	const int cnt0 = a.lcnt[id];
+	bool useList = false;
+	if (cnt0 >= 0 && !a.walkAlways) {
+		const float ox = x - a.lx0[id], oy = y - a.ly0[id], oz = z - a.lz0[id];
+		const float dl = a.ldelta[id];
+		useList = (ox * ox + oy * oy + oz * oz) * 1.0001f <= dl * dl;
+	}
+	if (!useList) { // drifted past the margin (or no list yet): the refresh kernel takes this step
+		if (lane == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id;
+		return;
+	}
+	const float T = __uint_as_float(a.dT[0]);
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	float rmin = 3.0e38f;
+	const uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP;
+	// both halves of a scatterer's 32-byte record (one L2 sector) are fetched together
+	for (int s0 = 0; s0 < cnt0; s0 += 32) {
+		const int s = s0 + lane;
+		if (s < cnt0) {
+			const uint32_t e = list[s];
+			const float4 p = a.entRec[2 * (size_t)e];
+			const float4 q = a.entRec[2 * (size_t)e + 1];
+			// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
+			const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+			const float d2 = dist2_rn(dx, dy, dz);
+			if (d2 < p.w && q.z >= T) ACC_HIT(dx, dy, dz, d2, q);
+		}
+	}
+	finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
+}
+
+__global__ void __launch_bounds__(REFRESH_WARPS * 32) k_list_refresh(const StepArgs a)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t wi = blockIdx.x * REFRESH_WARPS + (threadIdx.x >> 5);
+	if (wi >= *a.queueCount) return;
+	const uint32_t id = a.queue[wi];
+	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+	const float T = __uint_as_float(a.dT[0]);
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	float rmin = 3.0e38f;
+	uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP; // lists exist for this shard's movers only
+	const float delta = fminf(fmaxf(a.lhmin[id], 2.0f * a.fStep), 64.0f * a.fStep); // lhmin = margin to use
+	const float delta2 = delta * delta;
+	int nHit = 0;
+	int cnt = 0;
+	bool overflow = false;
+	// one scatterer per lane: hit test for this step, candidate test for the list.
+	// candidate <=> d <= h + delta <=> u = d2 - h^2 - delta^2 <= 2 h delta (no square root; 1e-4 slack)
+#define LIST_PROCESS(e_, p)                                                                            \
+	{                                                                                              \
+		const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);    \
+		const float d2 = dist2_rn(dx, dy, dz);                                                 \
+		const float u = d2 - p.w - delta2;                                                     \
+		bool cand = p.w > 0.0f && (u <= 0.0f || u * u <= 4.0004f * p.w * delta2);              \
+		if (cand) {                                                                            \
+			const float4 q = a.entNR[e_];                                                  \
+			cand = q.z >= T; /* dead scatterers never come back */                         \
+			if (cand && d2 < p.w) {                                                        \
+				ACC_HIT(dx, dy, dz, d2, q);                                            \
+				++nHit;                                                                \
+				if (a.touched) a.touched[e_] = 1;                                      \
+			}                                                                              \
+		}                                                                                      \
+		const uint32_t cm = __ballot_sync(SK_FULL, cand);                                      \
+		const int nc = __popc(cm);                                                             \
+		if (cnt + nc <= LIST_CAP) {                                                            \
+			if (cand) list[cnt + __popc(cm & lt)] = e_;                                    \
+		} else overflow = true;                                                                \
+		cnt += nc;                                                                             \
+	}
+	int lev = a.tv.top - 1;
+	uint32_t node = 0, mymask = 0;
+	const float bx0 = x - delta, bx1 = x + delta, by0 = y - delta, by1 = y + delta, bz0 = z - delta, bz1 = z + delta;
+#define LIST_TEST_CHILDREN()                                                                           \
+	{                                                                                              \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		float4 lo = bx[0], hi = bx[1];                                                         \
+		bool in_ = bx1 >= lo.x && bx0 <= hi.x && by1 >= lo.y && by0 <= hi.y && bz1 >= lo.z && bz0 <= hi.z && \
+		           lo.w >= T;                                                                  \
+		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+	LIST_TEST_CHILDREN();
+	while (true) {
+		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
+		if (m == 0) {
+			++lev;
+			if (lev >= a.tv.top) break;
+			node >>= 5;
+			continue;
+		}
+		int c = __ffs(m) - 1;
+		m &= m - 1;
+		if (lev > 0) {
+			if (lane == lev) mymask = m;
+			uint32_t child = node * 32 + c;
+			--lev;
+			node = child;
+			LIST_TEST_CHILDREN();
+			continue;
+		}
+		// leaf level: take two buckets per round so that two record loads are in flight
+		const uint32_t e0 = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+		const float4 p0 = a.entPos[e0];
+		if (m) {
+			const int c1 = __ffs(m) - 1;
+			m &= m - 1;
+			const uint32_t e1 = (node * 32 + c1) * 32 + lane;
+			const float4 p1 = a.entPos[e1];
+			if (lane == 0) mymask = m;
+			LIST_PROCESS(e0, p0);
+			LIST_PROCESS(e1, p1);
+		} else {
+			if (lane == 0) mymask = m;
+			LIST_PROCESS(e0, p0);
+		}
+	}
+#undef LIST_TEST_CHILDREN
+#undef LIST_PROCESS
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) nHit += __shfl_xor_sync(SK_FULL, nHit, o);
+	if (lane == 0) {
+		a.lcnt[id] = overflow ? -1 : cnt;
+		a.lx0[id] = x;
+		a.ly0[id] = y;
+		a.lz0[id] = z;
+		a.ldelta[id] = delta;
+		// feedback on the margin: grow it while the list stays short relative to the hits, shrink it
+		// when the list is long (a long list makes every step slower, a short one refreshes often)
+		float next = delta;
+		if (overflow || (float)cnt > a.polShrink * nHit + 32.0f) next = 0.6f * delta;
+		else if ((float)cnt < a.polGrow * nHit + 32.0f && cnt < a.polGrowMax) next = 1.5f * delta;
+		a.lhmin[id] = next;
+	}
+	finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
+}
+
 // After a step: adopt the new threshold (ScatterCut, smooth1.c:509-513).  If nothing was hit the
 // reference's fScatDens stays 0.0 and nothing is cut.
 __global__ void k_update_T(uint32_t *dT, int bNoPrune)
@@ -418,13 +469,17 @@ __global__ void k_update_T(uint32_t *dT, int bNoPrune)
 	uint32_t nx = dT[1];
 	if (!bNoPrune && nx != T_NONE) dT[0] = nx;
 	dT[1] = T_NONE;
+	dT[2] = 0u; // refresh queue of the next step
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
-__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float4 *entNR)
+__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float4 *entNR, float4 *entRec)
 {
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
-	if (e < nEnt && !touched[e]) entNR[e].z = 0.0f;
+	if (e < nEnt && !touched[e]) {
+		entNR[e].z = 0.0f;
+		entRec[2 * (size_t)e + 1].z = 0.0f;
+	}
 }
 
 // nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517)
@@ -493,6 +548,7 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tv = tree_view(c.treeE);
 	sa.entPos = c.entPos.p;
 	sa.entNR = c.entNR.p;
+	sa.entRec = c.entRec.p;
 	sa.touched = nullptr;
 	sa.mx = c.mx.p;
 	sa.my = c.my.p;
@@ -531,6 +587,8 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.polGrow = pol[1];
 	sa.polGrowMax = (int)pol[2];
 	c.listInitFactor = pol[3];
+	sa.queue = c.mQueue.p;
+	sa.queueCount = c.dT.p ? c.dT.p + 2 : nullptr;
 }
 
 static int count_scatterers(skidgpu_ctx &c)
@@ -547,7 +605,7 @@ static int count_scatterers(skidgpu_ctx &c)
 }
 
 // SKIDGPU_MOVE_KERNEL=warp selects the v1 kernel (a tree walk every step; kept for A/B
-// measurements); default = walk + candidate lists.
+// measurements); default = candidate lists.
 bool use_list_kernel();
 bool use_list_kernel()
 {
@@ -566,9 +624,11 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 		launched = 1;
 		sa.act = c.actList.p;
 		sa.nActive = c.nActive;
-		if (use_list_kernel())
-			SK_LAUNCH(k_move_list, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
-		else
+		if (use_list_kernel()) {
+			SK_LAUNCH(k_list_eval, (unsigned)ceil_div(c.nActive, EVAL_WARPS), EVAL_WARPS * 32, 0, c.stream, sa);
+			// grid sized for the worst case (everybody refreshes); warps beyond the queue length exit at once
+			SK_LAUNCH(k_list_refresh, (unsigned)ceil_div(c.nActive, REFRESH_WARPS), REFRESH_WARPS * 32, 0, c.stream, sa);
+		} else
 			SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
 		c.moverSteps += c.nActive;
 	}
@@ -604,7 +664,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.haveCenters = false;
 	const int m = c.nMove;
 	uint32_t *dT = c.dT.alloc(4);
-	uint32_t initT[2] = {0u, T_NONE};
+	uint32_t initT[3] = {0u, T_NONE, 0u}; // threshold, running min of this step, refresh-queue length
 	CK(cudaMemcpyAsync(dT, initT, sizeof initT, cudaMemcpyHostToDevice, s));
 	c.shardLo = (int)((long long)m * c.rank / c.nranks);
 	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
@@ -629,6 +689,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.lhmin.alloc(m);
 		c.lcnt.alloc(m);
 		if (use_list_kernel()) c.mList.alloc((size_t)(c.shardHi - c.shardLo > 0 ? c.shardHi - c.shardLo : 1) * LIST_CAP);
+		c.mQueue.alloc(c.shardHi - c.shardLo > 0 ? c.shardHi - c.shardLo : 1);
 		SK_LAUNCH(k_init_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeM.perm.p, fileIdx, c.x.p, c.y.p,
 		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p, c.ball2.p, c.lhmin.p, c.lcnt.p, c.listInitFactor);
 		c.actList.alloc(m);
@@ -662,7 +723,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	kt.stop(one_step(c, sa, bNoPrune));
 	if (bInitial && c.nEnt > 0) sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
 	if (bInitial && c.nEnt > 0)
-		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p);
+		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p);
 	sa.touched = nullptr;
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
 	if (c.keepStep0 && c.nEnt > 0) {
