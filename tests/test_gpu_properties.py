@@ -1,0 +1,157 @@
+"""Size-independent properties of the CUDA path at sizes where the oracle is too slow (2^20 here; the
+same checks hold at BASELINE's 2^24/2^27), plus edge cases: non-periodic input, no movers at all,
+nSmooth variants, native-format input through the host driver."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle.refdump import canonical_labels
+from skid_b200 import api, synth, tipsy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    snap = synth.make_box(1 << 20, seed=99, kind="dark")
+    res = api.run_skid(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"], **snap["flags"])
+    return snap, res
+
+
+def test_density_and_ball_properties(big):
+    snap, res = big
+    rho, b2 = res["rho"], res["ball2"]
+    assert np.all(np.isfinite(rho)) and np.all(rho > 0) and np.all(b2 > 0)
+    # mean density of a unit-mass unit box is 1: the SPH estimate is biased high by clustering but the
+    # mass-weighted mean of 1/rho (specific volume) must be close to the box volume
+    assert 0.5 < np.mean(1.0 / rho.astype(np.float64)) < 1.5
+    # the ball of a particle holds exactly nSmooth particles: check a sample by brute force (periodic)
+    p = snap["pinit"]["r"].astype(np.float32)
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, len(p), 24):
+        d = p - p[i]
+        d -= np.round(d)
+        d2 = (d.astype(np.float64) ** 2).sum(axis=1)
+        assert abs(int((d2 <= float(b2[i]) * (1 + 1e-6)).sum()) - 64) <= 1, i
+
+
+def test_group_catalogue_consistency(big):
+    snap, res = big
+    grp, cat = res["grp"], res["cat"]
+    n = len(grp)
+    ng = len(cat) - 1
+    assert grp.min() == 0 and grp.max() == ng
+    counts = np.bincount(grp, minlength=ng + 1)
+    assert np.array_equal(counts, cat["nMembers"])
+    assert counts[1:].min() >= snap["flags"]["nMembers"]                 # kdTooSmall
+    mass = np.bincount(grp, weights=snap["pinit"]["fMass"].astype(np.float64), minlength=ng + 1)
+    assert np.allclose(mass[1:], cat["fMass"][1:], rtol=1e-4)               # bound mass = sum of members
+    # FoF ids are canonical (ascending smallest member index); kdTooSmall keeps that order (kd.c:1249)
+    fof = res["fof_grp"]
+    assert np.array_equal(canonical_labels(fof), fof)
+    kept = grp > 0
+    pairs = np.unique(np.stack([grp[kept], fof[kept]], axis=1), axis=0)
+    assert len(pairs) == ng and np.all(np.diff(pairs[:, 1]) > 0)              # one FoF id per final id, same order
+    # members are movers: every grouped particle passed the density cut
+    assert np.all(res["rho"][grp > 0] >= np.float32(snap["flags"]["fDensMin"]))
+    # the FoF catalogue is coarser than the final one: unbinding only removes members
+    assert np.all((grp == 0) | (fof > 0))
+    assert res["nGroupBefore"] >= ng and res["nUnbound"] > 0
+    # group centres lie inside the box, radii are positive and smaller than half the box
+    assert np.all(np.abs(cat["rCenter"][1:]) <= 0.5) and np.all(cat["fRadius"][1:] > 0) and np.all(cat["fRadius"][1:] < 0.5)
+
+
+def test_fof_separation_property(big):
+    """No two movers of different FoF groups are closer than tau (checked on the converged positions
+    of a sample of groups by brute force)."""
+    snap, _ = big
+    fl = snap["flags"]
+    tau = float(np.float32(fl["tau"]))
+    sk = api.SkidGPU((1.0,) * 3, (0.0,) * 3, bPeriodic=True)
+    sk.set_particles(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"])
+    sk.smDensityInit(64, want_arrays=False)
+    fCvg = float(np.float32(0.5 * tau))
+    sk.move(fl["fDensMin"], fCvg=fCvg, fStep=float(np.float32(0.5 * fCvg)))
+    iord, r = sk.moved()
+    sk.kdFoF(tau)
+    grp, cat = sk.kdCalcCenter()
+    sk.close()
+    lab = grp[iord]
+    assert np.all(lab > 0)                      # every mover is in a group
+    rng = np.random.default_rng(1)
+    order = np.argsort(r[:, 0])
+    xs = r[order, 0]
+    for g in rng.integers(1, len(cat), 40):
+        mem = r[lab == g]
+        lo, hi = np.searchsorted(xs, [mem[:, 0].min() - tau, mem[:, 0].max() + tau])
+        near = order[lo:hi]
+        near = near[lab[near] != g]
+        if len(near) == 0 or len(mem) * len(near) > 4e7:
+            continue
+        d = mem[:, None, :].astype(np.float64) - r[near][None, :, :]
+        d2 = (d ** 2).sum(axis=2)
+        assert d2.min() >= tau * tau * (1 - 1e-6), g
+
+
+def test_rerun_is_deterministic(big):
+    snap, res = big
+    res2 = api.run_skid(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"], want_arrays=False, **snap["flags"])
+    assert np.array_equal(res["grp"], res2["grp"])
+    assert res["nUnbound"] == res2["nUnbound"] and res["nIttr"] == res2["nIttr"]
+
+
+def test_edge_cases():
+    # (a) no particle passes the density cut: nGroup = 1, everything in group 0 (kd.c:815-823)
+    snap = synth.make_box(4096, seed=5)
+    fl = dict(snap["flags"], fDensMin=1e30)
+    res = api.run_skid(snap["pinit"], 0, 4096, 0, **fl)
+    assert res["nMove"] == 0 and res["nGroup"] == 0 and not res["grp"].any()
+    # (b) not periodic (fPeriod = FLT_MAX, main.c:125-128): no replicas, still finds groups
+    fl = dict(snap["flags"])
+    fl.pop("period")
+    res = api.run_skid(snap["pinit"], 0, 4096, 0, period=None, **fl)
+    assert res["nExtraScat"] == 0 and res["nMove"] > 0 and res["nGroup"] > 0
+    # (c) nSmooth below / at one warp and the upper limit; fBall2 grows with k
+    sk = api.SkidGPU((1.0,) * 3, (0.0,) * 3, bPeriodic=True)
+    sk.set_particles(snap["pinit"], 0, 4096, 0)
+    prev = None
+    for k in (8, 32, 33, 64):
+        rho, b2 = sk.smDensityInit(k)
+        assert np.all(b2 > 0)
+        if prev is not None:
+            assert np.all(b2 >= prev)
+        prev = b2
+    with pytest.raises(api.SkidError):
+        sk.smDensityInit(65)
+    with pytest.raises(api.SkidError):
+        sk.smDensityInit(0)
+    sk.close()
+    # (d) fewer scatter-active particles than nSmooth (smooth1.c:12)
+    tiny = synth.make_box(40, seed=1)
+    sk = api.SkidGPU((1.0,) * 3, (0.0,) * 3, bPeriodic=True)
+    sk.set_particles(tiny["pinit"], 0, 40, 0)
+    with pytest.raises(api.SkidError, match="nSmooth"):
+        sk.smDensityInit(64)
+    sk.close()
+
+
+def test_native_format_input(tmp_path):
+    """The host driver reads native TIPSY (no -std) and gives the same groups as from the XDR file."""
+    snap = synth.make_box(1 << 13, seed=21, kind="gasdark")
+    gas, dark, star = tipsy.pinit_to_records(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"])
+    outs = {}
+    for std in (True, False):
+        f = str(tmp_path / ("in.std" if std else "in.bin"))
+        tipsy.write_tipsy(f, 1.0, gas, dark, star, standard=std)
+        args = [a for a in snap["ref_args"] if a != "-std"] + (["-std"] if std else [])
+        with open(f, "rb") as fin:
+            r = subprocess.run([os.path.join(ROOT, "host", "skid")] + args + ["-o", str(tmp_path / ("s" if std else "n"))],
+                               stdin=fin, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[std] = tipsy.read_array(str(tmp_path / ("s.grp" if std else "n.grp")))
+        gtp = tipsy.read_gtp(str(tmp_path / ("s.gtp" if std else "n.gtp")), standard=std)
+        assert len(gtp["mass"]) == int(outs[std].max())
+    assert np.array_equal(outs[True], outs[False])
