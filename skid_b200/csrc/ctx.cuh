@@ -59,6 +59,12 @@ struct skidgpu_ctx {
 	DevBuf<int> lcnt;
 	float listInitFactor = 0.3f;
 	DevBuf<uint32_t> mQueue; // movers that refresh their list this step
+	// tiles: TILE consecutive entries of the position-sorted active list share one scatterer list (move.cu)
+	int nTiles = 0, tileStepsLeft = 0, tileWindow = 5, tileBuilds = 0;
+	DevBuf<uint64_t> tKeys;
+	DevBuf<uint32_t> tList;
+	DevBuf<float4> tPos;
+	DevBuf<int> tCnt;
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step

@@ -122,145 +122,58 @@ struct StepArgs {
 	int polGrowMax;
 	uint32_t *queue;      // movers whose list must be refreshed this step
 	uint32_t *queueCount; // = dT + 2, reset by k_update_T
+	float wrapHiF[3], wrapLoF[3]; // largest floats <= wrapHi / wrapLo: same decisions as the double compares
+	// tiles (k_tile_build / k_tile_step): TILE consecutive entries of the position-sorted active list
+	uint32_t *tList; // TILE_CAP scatterer indices per tile
+	float4 *tPos;    // per active slot: position at the last rebuild, reach
+	int *tCnt;       // per tile: list length, -1 = overflow (members walk the tree themselves)
 };
 
-constexpr int STEP_WARPS = 8;
-
-__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a)
-{
-	const int lane = threadIdx.x & 31;
-	const int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
-	if (wi >= a.nActive) return;
-	const uint32_t id = a.act[wi];
-	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
-	const float T = __uint_as_float(a.dT[0]);
-	float ax = 0.0f, ay = 0.0f, az = 0.0f;
-	float rmin = 3.0e38f;
-
-	int lev = a.tv.top - 1;
-	uint32_t node = 0;
-	uint32_t mymask = 0;
-#define STEP_TEST_CHILDREN()                                                                           \
-	{                                                                                              \
-		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
-		float4 lo = bx[0], hi = bx[1];                                                         \
-		bool in_ = x >= lo.x && x <= hi.x && y >= lo.y && y <= hi.y && z >= lo.z && z <= hi.z && \
-		           lo.w >= T;                                                                  \
-		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
-		if (lane == lev) mymask = m_;                                                          \
-	}
-	STEP_TEST_CHILDREN();
-	while (true) {
-		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
-		if (m == 0) {
-			++lev;
-			if (lev >= a.tv.top) break;
-			node >>= 5;
-			continue;
-		}
-		int c = __ffs(m) - 1;
-		m &= m - 1;
-		if (lane == lev) mymask = m;
-		uint32_t child = node * 32 + c;
-		if (lev > 0) {
-			--lev;
-			node = child;
-			STEP_TEST_CHILDREN();
-			continue;
-		}
-		int e = (int)child * 32 + lane;
-		if (e < a.nEnt) {
-			float4 p = a.entPos[e];
-			// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
-			float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
-			float d2 = dist2_rn(dx, dy, dz);
-			if (d2 < p.w) {
-				float4 nr = a.entNR[e];
-				if (nr.z >= T) {
-					// smAccDensity (smooth1.c:447-459)
-					float r2 = __fmul_rn(d2, nr.x);
-					float rs = __fsqrt_rn(r2);
-					if (r2 < 1.0f) rs = (float)(-3.0 + 2.25 * (double)rs);
-					else rs = (float)(-3.0 / (double)rs + 3.0 - 0.75 * (double)rs);
-					rs = __fmul_rn(rs, nr.y);
-					ax = __fadd_rn(ax, __fmul_rn(dx, rs));
-					ay = __fadd_rn(ay, __fmul_rn(dy, rs));
-					az = __fadd_rn(az, __fmul_rn(dz, rs));
-					rmin = fminf(rmin, nr.z);
-					if (a.touched) a.touched[e] = 1;
-				}
-			}
-		}
-	}
-#undef STEP_TEST_CHILDREN
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		ax += __shfl_xor_sync(SK_FULL, ax, o);
-		ay += __shfl_xor_sync(SK_FULL, ay, o);
-		az += __shfl_xor_sync(SK_FULL, az, o);
-		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
-	}
-	if (lane == 0) {
-		if (rmin < 3.0e38f) atomicMin(&a.dT[1], __float_as_uint(rmin)); // smooth1.c:460-461 (rho > 0)
-		if (a.a0x) {
-			a.a0x[id] = ax;
-			a.a0y[id] = ay;
-			a.a0z[id] = az;
-		}
-		// kdMoveParticles (kd.c:711-729)
-		float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
-		float ai = (float)sqrt((double)s2);
-		if (ai > 0.0f) ai = (float)((double)a.fStep / sqrt((double)s2));
-		else ai = 0.0f;
-		float r[3] = {__fsub_rn(x, __fmul_rn(ai, ax)), __fsub_rn(y, __fmul_rn(ai, ay)),
-		              __fsub_rn(z, __fmul_rn(ai, az))};
-#pragma unroll
-		for (int j = 0; j < 3; ++j) {
-			if ((double)r[j] > a.wrapHi[j]) r[j] = __fsub_rn(r[j], a.L[j]);
-			if ((double)r[j] <= a.wrapLo[j]) r[j] = __fadd_rn(r[j], a.L[j]);
-		}
-		a.mx[id] = r[0];
-		a.my[id] = r[1];
-		a.mz[id] = r[2];
-	}
-}
-
-// kdMoveParticles (kd.c:711-729) for one mover
+// kdMoveParticles (kd.c:711-729) for one mover.  The reference forms ai = fStep/sqrt(|a|^2) in double and
+// rounds it to float; here a refined float reciprocal square root gives the same value to <= 2 ulp
+// (a position change of ~1e-7 fStep, far below the float spacing of the coordinates), and the wrap
+// compares use the largest floats <= centre +- L/2, which decide exactly like the double compares.
 __device__ __forceinline__ void move_one(const StepArgs &a, uint32_t id, float x, float y, float z, float ax, float ay,
                                          float az)
 {
-	float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
-	float ai = (float)sqrt((double)s2);
-	if (ai > 0.0f) ai = (float)((double)a.fStep / sqrt((double)s2));
-	else ai = 0.0f;
+	const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+	float ai;
+	if (s2 > 1.0e-30f && s2 < 1.0e30f) {
+		float yv = rsqrtf(s2);
+		yv = yv * fmaf(-0.5f * s2, yv * yv, 1.5f); // one Newton step
+		ai = a.fStep * yv;
+	} else { // zero, denormal, huge or non-finite: the reference's own arithmetic
+		ai = (float)sqrt((double)s2);
+		if (ai > 0.0f) ai = (float)((double)a.fStep / sqrt((double)s2));
+		else ai = 0.0f;
+	}
 	float r[3] = {__fsub_rn(x, __fmul_rn(ai, ax)), __fsub_rn(y, __fmul_rn(ai, ay)), __fsub_rn(z, __fmul_rn(ai, az))};
 #pragma unroll
 	for (int j = 0; j < 3; ++j) {
-		if ((double)r[j] > a.wrapHi[j]) r[j] = __fsub_rn(r[j], a.L[j]);
-		if ((double)r[j] <= a.wrapLo[j]) r[j] = __fadd_rn(r[j], a.L[j]);
+		if (r[j] > a.wrapHiF[j]) r[j] = __fsub_rn(r[j], a.L[j]);
+		if (r[j] <= a.wrapLoF[j]) r[j] = __fadd_rn(r[j], a.L[j]);
 	}
 	a.mx[id] = r[0];
 	a.my[id] = r[1];
 	a.mz[id] = r[2];
 }
 
-// smAccDensity (smooth1.c:447-459) for one hit.  Same float32 operations as the reference
-// (r2 = d2*ih2, rs = sqrt(r2), rs *= fNorm, a += dx*rs, all round-to-nearest, no FMA on the sums);
-// the spline factor, which the reference evaluates in double and rounds to float, is formed with
-// one FMA (inner branch, a single rounding of the exact value) or with a float division plus its
-// exact-remainder correction (outer branch), i.e. to float accuracy without double arithmetic.
+// smAccDensity (smooth1.c:447-459) for one hit: r2 = d2*ih2, rs = sqrt(r2), spline factor, rs *= fNorm,
+// a += dx*rs.  The reference evaluates the factor in double from the float rs and rounds it to float;
+// here rs and 1/rs come from one MUFU.RSQ refined by a Newton step each (~1 ulp) and the factor is
+// formed with FMAs, i.e. to float accuracy without the IEEE sqrt/div sequences (ncu: they were 40 % of
+// the instructions of a step).  d2 = 0 (a mover sitting on a scatterer) gives rs = 0, factor -3, as in
+// the reference.
 #define ACC_HIT(dx, dy, dz, d2, q)                                                                     \
 {                                                                                              \
 	const float r2_ = __fmul_rn((d2), (q).x);                                              \
-	const float rs_ = __fsqrt_rn(r2_);                                                     \
-	float g_;                                                                              \
-	if (r2_ < 1.0f) g_ = fmaf(2.25f, rs_, -3.0f);                                          \
-	else {                                                                                 \
-		const float t_ = __fdiv_rn(-3.0f, rs_);                                        \
-		const float c_ = __fdividef(fmaf(-t_, rs_, -3.0f), rs_);                       \
-		g_ = fmaf(-0.75f, rs_, 3.0f + t_) + c_;                                        \
-	}                                                                                      \
-	g_ = __fmul_rn(g_, (q).y);                                                             \
+	float y_ = rsqrtf(fmaxf(r2_, 1.0e-30f));                                               \
+	float rs_ = r2_ * y_;                                                                  \
+	rs_ = fmaf(0.5f * y_, fmaf(-rs_, rs_, r2_), rs_);                                      \
+	y_ = fmaf(y_, fmaf(-rs_, y_, 1.0f), y_);                                               \
+	const float gi_ = fmaf(2.25f, rs_, -3.0f);                                             \
+	const float go_ = fmaf(-0.75f, rs_, fmaf(-3.0f, y_, 3.0f));                            \
+	const float g_ = __fmul_rn(r2_ < 1.0f ? gi_ : go_, (q).y);                             \
 	ax = __fadd_rn(ax, __fmul_rn((dx), g_));                                               \
 	ay = __fadd_rn(ay, __fmul_rn((dy), g_));                                               \
 	az = __fadd_rn(az, __fmul_rn((dz), g_));                                               \
@@ -316,51 +229,375 @@ __device__ __forceinline__ void finish_step(const StepArgs &a, uint32_t id, floa
 	}
 }
 
-__global__ void __launch_bounds__(EVAL_WARPS * 32, 16) k_list_eval(const StepArgs a)
+// One list entry: the reference's float32 hit test (smBallGather, smooth1.c:365-369: dx = x_scatterer -
+// x_mover, no FMA) and, on a hit, smAccDensity.
+#define EVAL_ENTRY(p, q)                                                                               \
+	{                                                                                              \
+		const float dx = __fsub_rn((p).x, x), dy = __fsub_rn((p).y, y), dz = __fsub_rn((p).z, z); \
+		const float d2 = dist2_rn(dx, dy, dz);                                                 \
+		if (d2 < (p).w && (q).z >= T) ACC_HIT(dx, dy, dz, d2, q);                              \
+	}
+
+// ncu on the first split version (profiles/r01_v3_eval_*): no unit busy, 34 stall cycles per issued
+// instruction on the dependent chain active list -> mover state -> list -> scatterer records, each
+// hop a full L2/DRAM latency.  Here the first list chunk is requested together with the mover state
+// (its address depends only on the mover id; stale or unused slots are clamped to valid indices), and
+// the list is consumed 64 entries at a time with the index loads of the next chunk and both record
+// gathers of this chunk in flight before the first use.
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 10) k_list_eval(const StepArgs a)
 {
 	const int lane = threadIdx.x & 31;
 	const int wi = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
 	if (wi >= a.nActive) return;
 	const uint32_t id = a.act[wi];
+	const uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP;
+	const uint32_t emax = (uint32_t)a.nEnt - 1u;
+	uint32_t ea = list[lane], eb = list[32 + lane];
 	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
 	const int cnt0 = a.lcnt[id];
-	bool useList = false;
-	if (cnt0 >= 0 && !a.walkAlways) {
-		const float ox = x - a.lx0[id], oy = y - a.ly0[id], oz = z - a.lz0[id];
-		const float dl = a.ldelta[id];
-		useList = (ox * ox + oy * oy + oz * oz) * 1.0001f <= dl * dl;
-	}
-	if (!useList) { // drifted past the margin (or no list yet): the refresh kernel takes this step
+	const float ox = x - a.lx0[id], oy = y - a.ly0[id], oz = z - a.lz0[id];
+	const float dl = a.ldelta[id];
+	const float T = __uint_as_float(a.dT[0]);
+	const bool useList = cnt0 >= 0 && !a.walkAlways && (ox * ox + oy * oy + oz * oz) * 1.0001f <= dl * dl;
+	if (!useList) { // drifted past the margin (or no list yet): the refresh kernels take this step
 		if (lane == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id;
 		return;
 	}
-	const float T = __uint_as_float(a.dT[0]);
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
 	float rmin = 3.0e38f;
-	const uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP;
-	// both halves of a scatterer's 32-byte record (one L2 sector) are fetched together
-	for (int s0 = 0; s0 < cnt0; s0 += 32) {
-		const int s = s0 + lane;
-		if (s < cnt0) {
-			const uint32_t e = list[s];
-			const float4 p = a.entRec[2 * (size_t)e];
-			const float4 q = a.entRec[2 * (size_t)e + 1];
-			// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
-			const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
-			const float d2 = dist2_rn(dx, dy, dz);
-			if (d2 < p.w && q.z >= T) ACC_HIT(dx, dy, dz, d2, q);
+	for (int s0 = 0; s0 < cnt0; s0 += 64) {
+		// both halves of a scatterer's 32-byte record (one sector) are fetched together
+		ea = min(ea, emax);
+		float4 pa = a.entRec[2 * (size_t)ea];
+		const float4 qa = a.entRec[2 * (size_t)ea + 1];
+		const bool two = s0 + 32 < cnt0;
+		float4 pb = make_float4(0.0f, 0.0f, 0.0f, -1.0f), qb = pb;
+		if (two) {
+			eb = min(eb, emax);
+			pb = a.entRec[2 * (size_t)eb];
+			qb = a.entRec[2 * (size_t)eb + 1];
 		}
+		if (s0 + 64 < cnt0) { // cnt0 <= LIST_CAP, a multiple of 64
+			ea = list[s0 + 64 + lane];
+			eb = list[s0 + 96 + lane];
+		}
+		if (s0 + lane >= cnt0) pa.w = -1.0f;
+		if (s0 + 32 + lane >= cnt0) pb.w = -1.0f;
+		EVAL_ENTRY(pa, qa);
+		if (two) EVAL_ENTRY(pb, qb);
 	}
 	finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
 }
 
-__global__ void __launch_bounds__(REFRESH_WARPS * 32) k_list_refresh(const StepArgs a)
+// ------------------------------------------------------------------------------------------------
+// Default path: tiles.  ncu on the list kernels (profiles/r01_v3_eval_*, r01_v4_*): every unit idle,
+// yet 1.1-1.4 ns per mover-step - the per-mover gathers of ~200 scatterer records are 32 different
+// 128-byte lines per load instruction, and the L1 tag stage retires about one such line per clock
+// and SM (l1tex__t_sectors / cycle = 0.8).  Scattered record fetches, not DRAM bytes and not issue
+// slots, are the currency of this stage; sharing them between movers is the only way down.
+//
+//  * Every 5 steps (kdPruneInactive's rhythm) the ACTIVE movers are sorted by the Morton key of
+//    their current position and cut into tiles of TILE consecutive movers: compact by construction,
+//    no idle slots as movers freeze.
+//  * k_tile_build (one warp per tile): one tree walk collects every scatterer whose ball comes within
+//    `reach` of a member, reach = the distance a mover can travel before the next rebuild (a step
+//    moves a mover by exactly fStep, kd.c:716-721).  Until then the list is complete for every
+//    member, so no validity bookkeeping is needed at all.
+//  * k_tile_step (one block per tile, one warp per mover, every step): the tile's records are fetched
+//    ONCE (TILE x fewer scattered fetches per mover-step) into shared memory, then every warp runs
+//    the reference's float32 hit test for its mover against the staged records.
+//  * Movers that leave their ball (a periodic wrap moves them by L) and tiles whose list overflows TILE_CAP
+//    (members on both sides of a Morton discontinuity) take the step with their own tree walk
+//    (k_move_step on a queue).
+// Hit set, hit test and pruning rule are those of the reference (and of the v1 kernel).
+constexpr int TILE = 8;       // movers per tile = warps per block
+#ifndef TILE_CAP_
+#define TILE_CAP_ 1024
+#endif
+constexpr int TILE_CAP = TILE_CAP_; // scatterers per tile list
+constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
+
+__device__ __forceinline__ uint64_t spread21m(uint32_t v)
+{
+	uint64_t x = v & 0x1fffffu;
+	x = (x | (x << 32)) & 0x1f00000000ffffull;
+	x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+	x = (x | (x << 8)) & 0x100f00f00f00f00full;
+	x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+	x = (x | (x << 2)) & 0x1249249249249249ull;
+	return x;
+}
+
+// 63-bit Morton key of the current position of every active mover (bbox = box of the initial positions)
+__global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t *act, const float *mx, const float *my,
+                                                    const float *mz, const float *bbox, uint64_t *keys, uint32_t *vals)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nActive) return;
+	const uint32_t id = act[i];
+	const float p[3] = {mx[id], my[id], mz[id]};
+	uint32_t q[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		const float ext = bbox[3 + d] - bbox[d];
+		float t = ext > 0.0f ? (p[d] - bbox[d]) / ext : 0.0f;
+		t = fminf(fmaxf(t, 0.0f), 1.0f);
+		q[d] = min((uint32_t)(t * 2097152.0f), 2097151u);
+	}
+	keys[i] = (spread21m(q[2]) << 2) | (spread21m(q[1]) << 1) | spread21m(q[0]);
+	vals[i] = id;
+}
+
+// one warp per tile: one tree walk collects the union of the members' candidate sets - every scatterer
+// with |x_e - x_m| <= h_e + reach for some member m, reach = the distance a mover can travel before the
+// next rebuild.  Nodes and leaf buckets are pruned against the members themselves (not only against
+// their bounding box): a tile that straddles a Morton discontinuity still gets a short list.
+__global__ void __launch_bounds__(128) k_tile_build(const StepArgs a, int nTiles, float reach)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1u;
+	const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (t >= nTiles) return;
+	const float T = __uint_as_float(a.dT[0]);
+	float mxv[TILE], myv[TILE], mzv[TILE];
+	float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f, z0 = 3.0e38f, z1 = -3.0e38f;
+#pragma unroll
+	for (int m = 0; m < TILE; ++m) {
+		const int mi = min(t * TILE + m, a.nActive - 1); // a short last tile repeats its last member
+		const uint32_t id = a.act[mi];
+		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
+		x0 = fminf(x0, mxv[m]), x1 = fmaxf(x1, mxv[m]);
+		y0 = fminf(y0, myv[m]), y1 = fmaxf(y1, myv[m]);
+		z0 = fminf(z0, mzv[m]), z1 = fmaxf(z1, mzv[m]);
+	}
+	// slack for the rounding of the moves and of the tests below
+	const float r = reach * 1.001f + 4.0e-7f * fmaxf(fmaxf(fabsf(x0), fabsf(x1)),
+	                                                 fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(z0), fabsf(z1))));
+	const float r2 = r * r;
+	if (lane < TILE && t * TILE + lane < a.nActive) {
+		float px = mxv[0], py = myv[0], pz = mzv[0];
+#pragma unroll
+		for (int m = 1; m < TILE; ++m)
+			if (lane == m) px = mxv[m], py = myv[m], pz = mzv[m];
+		a.tPos[t * TILE + lane] = make_float4(px, py, pz, r);
+	}
+	x0 -= r, x1 += r, y0 -= r, y1 += r, z0 -= r, z1 += r;
+	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
+	int cnt = 0;
+	bool overflow = false;
+	int lev = a.tv.top - 1;
+	uint32_t node = 0, mymask = 0;
+#define TILE_TEST_CHILDREN()                                                                           \
+	{                                                                                              \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		const float4 lo = bx[0], hi = bx[1];                                                   \
+		bool in_ = x1 >= lo.x && x0 <= hi.x && y1 >= lo.y && y0 <= hi.y && z1 >= lo.z && z0 <= hi.z && \
+		           lo.w >= T;                                                                  \
+		if (in_) {                                                                             \
+			bool any_ = false;                                                             \
+			_Pragma("unroll") for (int m = 0; m < TILE; ++m)                               \
+			    any_ |= mxv[m] + r >= lo.x && mxv[m] - r <= hi.x && myv[m] + r >= lo.y && myv[m] - r <= hi.y && \
+			            mzv[m] + r >= lo.z && mzv[m] - r <= hi.z;                          \
+			in_ = any_;                                                                    \
+		}                                                                                      \
+		const uint32_t m_ = __ballot_sync(SK_FULL, in_);                                       \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+	// candidate <=> d <= h + r for the nearest member <=> u = d2 - h^2 - r^2 <= 2 h r (no square root;
+	// 1e-4 slack); dead scatterers never come back
+#define TILE_LEAF(e_, p)                                                                               \
+	{                                                                                              \
+		float d2_ = 3.0e38f;                                                                   \
+		_Pragma("unroll") for (int m = 0; m < TILE; ++m)                                       \
+		{                                                                                      \
+			const float dx = (p).x - mxv[m], dy = (p).y - myv[m], dz = (p).z - mzv[m];     \
+			d2_ = fminf(d2_, dx * dx + dy * dy + dz * dz);                                 \
+		}                                                                                      \
+		const float u_ = d2_ - (p).w - r2;                                                     \
+		bool cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);           \
+		if (cand) cand = a.entNR[e_].z >= T;                                                   \
+		const uint32_t cm = __ballot_sync(SK_FULL, cand);                                      \
+		const int nc = __popc(cm);                                                             \
+		if (cnt + nc > TILE_CAP) overflow = true;                                              \
+		else if (cand) list[cnt + __popc(cm & lt)] = e_;                                       \
+		cnt += nc;                                                                             \
+	}
+	TILE_TEST_CHILDREN();
+	while (!overflow) {
+		uint32_t mk = __shfl_sync(SK_FULL, mymask, lev);
+		if (mk == 0) {
+			++lev;
+			if (lev >= a.tv.top) break;
+			node >>= 5;
+			continue;
+		}
+		const int c = __ffs(mk) - 1;
+		mk &= mk - 1;
+		if (lev > 0) {
+			if (lane == lev) mymask = mk;
+			--lev;
+			node = node * 32 + c;
+			TILE_TEST_CHILDREN();
+			continue;
+		}
+		// leaf level: two buckets per round so that two record loads are in flight
+		const uint32_t e0 = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+		const float4 p0 = a.entPos[e0];
+		if (mk) {
+			const int c1 = __ffs(mk) - 1;
+			mk &= mk - 1;
+			const uint32_t e1 = (node * 32 + c1) * 32 + lane;
+			const float4 p1 = a.entPos[e1];
+			if (lane == 0) mymask = mk;
+			TILE_LEAF(e0, p0);
+			TILE_LEAF(e1, p1);
+		} else {
+			if (lane == 0) mymask = mk;
+			TILE_LEAF(e0, p0);
+		}
+	}
+#undef TILE_TEST_CHILDREN
+#undef TILE_LEAF
+	if (lane == 0) a.tCnt[t] = overflow ? -1 : cnt;
+}
+
+constexpr int TILE_CHUNK = 384; // records staged in shared memory at a time
+struct TileShared {
+	float4 p[TILE_CHUNK]; // (x,y,z,fBall2 or -1 when dead)
+	float4 q[TILE_CHUNK]; // (4/fBall2, fNorm, rho, 0)
+};
+
+__global__ void __launch_bounds__(TILE * 32, 8) k_tile_step(const StepArgs a)
+{
+	__shared__ TileShared sh;
+	__shared__ uint32_t sh_e[TILE_CHUNK];
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int t = blockIdx.x;
+	const int cnt = a.tCnt[t];
+	const int mi = t * TILE + w;
+	const bool have = mi < a.nActive;
+	const uint32_t id = have ? a.act[mi] : 0u;
+	float x = 0.0f, y = 0.0f, z = 0.0f;
+	if (have) x = a.mx[id], y = a.my[id], z = a.mz[id];
+	const float T = __uint_as_float(a.dT[0]);
+	bool inside = false;
+	if (have && cnt >= 0) { // still within reach of where the list was built? (a periodic wrap moves it by L)
+		const float4 b = a.tPos[mi];
+		const float ox = x - b.x, oy = y - b.y, oz = z - b.z;
+		inside = ox * ox + oy * oy + oz * oz <= b.w * b.w;
+	}
+	if (have && !inside) { // overflowed tile, or the mover left its ball: own tree walk
+		if (lane == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id;
+	}
+	const bool run = have && inside;
+	const uint32_t *list = a.tList + (size_t)t * TILE_CAP;
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	float rmin = 3.0e38f;
+	for (int c0 = 0; c0 < cnt; c0 += TILE_CHUNK) {
+		const int nc = min(cnt - c0, TILE_CHUNK);
+		if (c0) __syncthreads();
+		for (int s = threadIdx.x; s < nc; s += TILE * 32) {
+			const uint32_t e = list[c0 + s];
+			float4 p = a.entRec[2 * (size_t)e];
+			const float4 q = a.entRec[2 * (size_t)e + 1];
+			if (!(q.z >= T)) p.w = -1.0f; // pruned since the list was built
+			if (a.touched) sh_e[s] = e;
+			sh.p[s] = p;
+			sh.q[s] = q;
+		}
+		__syncthreads();
+		if (run) {
+			for (int s = lane; s < nc; s += 32) {
+				const float4 p = sh.p[s];
+				// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
+				const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+				const float d2 = dist2_rn(dx, dy, dz);
+				if (d2 < p.w) {
+					const float4 q = sh.q[s];
+					ACC_HIT(dx, dy, dz, d2, q);
+					if (a.touched) a.touched[sh_e[s]] = 1;
+				}
+			}
+		}
+	}
+	if (run) finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
+}
+
+// v1 kernel: one warp per mover walks the scatterer tree every step (profiles/r01_v1_move_*: issue
+// bound, ~3600 warp instructions per mover-step, 1500 scatterers tested for 85 hits).  Still used for
+// the movers a tile can not serve (queue filled by k_tile_step) and, with SKIDGPU_MOVE_KERNEL=warp,
+// for everything (A/B measurements).  countPtr == nullptr: the first `count` entries of `ids`.
+constexpr int STEP_WARPS = 8;
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a, const uint32_t *ids, int count,
+                                                               const uint32_t *countPtr)
+{
+	const int lane = threadIdx.x & 31;
+	const int n = countPtr ? (int)*countPtr : count;
+	const float T = __uint_as_float(a.dT[0]);
+	for (int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5); wi < n; wi += gridDim.x * STEP_WARPS) {
+		const uint32_t id = ids[wi];
+		const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+		float ax = 0.0f, ay = 0.0f, az = 0.0f;
+		float rmin = 3.0e38f;
+		int lev = a.tv.top - 1;
+		uint32_t node = 0;
+		uint32_t mymask = 0;
+#define STEP_TEST_CHILDREN()                                                                           \
+	{                                                                                              \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		float4 lo = bx[0], hi = bx[1];                                                         \
+		bool in_ = x >= lo.x && x <= hi.x && y >= lo.y && y <= hi.y && z >= lo.z && z <= hi.z && \
+		           lo.w >= T;                                                                  \
+		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+		STEP_TEST_CHILDREN();
+		while (true) {
+			uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
+			if (m == 0) {
+				++lev;
+				if (lev >= a.tv.top) break;
+				node >>= 5;
+				continue;
+			}
+			int c = __ffs(m) - 1;
+			m &= m - 1;
+			if (lane == lev) mymask = m;
+			uint32_t child = node * 32 + c;
+			if (lev > 0) {
+				--lev;
+				node = child;
+				STEP_TEST_CHILDREN();
+				continue;
+			}
+			const uint32_t e = child * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+			const float4 p = a.entPos[e];
+			// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
+			const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+			const float d2 = dist2_rn(dx, dy, dz);
+			if (d2 < p.w) {
+				const float4 q = a.entNR[e];
+				if (q.z >= T) {
+					ACC_HIT(dx, dy, dz, d2, q);
+					if (a.touched) a.touched[e] = 1;
+				}
+			}
+		}
+#undef STEP_TEST_CHILDREN
+		finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
+	}
+}
+
+// tree-walk refresh of the movers in `queue` (all queued movers without buckets, else those their
+// bucket can not serve)
+__global__ void __launch_bounds__(REFRESH_WARPS * 32) k_list_refresh(const StepArgs a, const uint32_t *queue,
+                                                                     const uint32_t *queueCount)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint32_t wi = blockIdx.x * REFRESH_WARPS + (threadIdx.x >> 5);
-	if (wi >= *a.queueCount) return;
-	const uint32_t id = a.queue[wi];
+	if (wi >= *queueCount) return;
+	const uint32_t id = queue[wi];
 	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
 	const float T = __uint_as_float(a.dT[0]);
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
@@ -469,7 +706,9 @@ __global__ void k_update_T(uint32_t *dT, int bNoPrune)
 	uint32_t nx = dT[1];
 	if (!bNoPrune && nx != T_NONE) dT[0] = nx;
 	dT[1] = T_NONE;
-	dT[2] = 0u; // refresh queue of the next step
+	dT[2] = 0u; // refresh queues of the next step: movers, buckets, tree-walk movers
+	dT[3] = 0u;
+	dT[4] = 0u;
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
@@ -589,6 +828,16 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	c.listInitFactor = pol[3];
 	sa.queue = c.mQueue.p;
 	sa.queueCount = c.dT.p ? c.dT.p + 2 : nullptr;
+	for (int d = 0; d < 3; ++d) { // r > t  <=>  r > (largest float <= t) for float r (same for <=)
+		float h = (float)sa.wrapHi[d], l = (float)sa.wrapLo[d];
+		if ((double)h > sa.wrapHi[d]) h = nextafterf(h, -INFINITY);
+		if ((double)l > sa.wrapLo[d]) l = nextafterf(l, -INFINITY);
+		sa.wrapHiF[d] = h;
+		sa.wrapLoF[d] = l;
+	}
+	sa.tList = c.tList.p;
+	sa.tPos = c.tPos.p;
+	sa.tCnt = c.tCnt.p;
 }
 
 static int count_scatterers(skidgpu_ctx &c)
@@ -604,17 +853,69 @@ static int count_scatterers(skidgpu_ctx &c)
 	return (int)h;
 }
 
-// SKIDGPU_MOVE_KERNEL=warp selects the v1 kernel (a tree walk every step; kept for A/B
-// measurements); default = candidate lists.
-bool use_list_kernel();
-bool use_list_kernel()
+// SKIDGPU_MOVE_KERNEL = tile (default) | list (per-mover candidate lists refreshed by tree walks) |
+// warp (v1: a tree walk per mover and step).  The last two are kept for A/B measurements.
+enum { MOVE_TILE = 0, MOVE_LIST = 1, MOVE_WARP = 2 };
+static int move_kernel()
 {
 	static int v = -1;
 	if (v < 0) {
 		const char *e = getenv("SKIDGPU_MOVE_KERNEL");
-		v = (e && !strcmp(e, "warp")) ? 0 : 1;
+		v = MOVE_TILE;
+		if (e && !strcmp(e, "warp")) v = MOVE_WARP;
+		if (e && !strcmp(e, "list")) v = MOVE_LIST;
 	}
-	return v == 1;
+	return v;
+}
+
+// Sort the active movers by position and build the tile lists; valid for `steps` steps of length fStep.
+static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
+{
+	cudaStream_t s = c.stream;
+	c.nTiles = 0;
+	c.tileStepsLeft = steps;
+	if (c.nActive <= 0 || c.nEnt <= 0) return;
+	// The active list starts in Morton order of the initial positions and compaction keeps its order, so
+	// tiles stay compact for a while: re-sort by current position only every few rebuilds (the lists are
+	// unions of per-member neighbourhoods - compactness is efficiency, never correctness).
+	static int every = -1;
+	if (every < 0) {
+		const char *e = getenv("SKIDGPU_TILE_SORT_EVERY");
+		every = e ? atoi(e) : 4;
+	}
+	if (every > 0 && c.tileBuilds % every == every - 1) {
+		uint64_t *keys = c.tKeys.alloc(c.nActive);
+		SK_LAUNCH(k_mover_keys, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
+		          c.my.p, c.mz.p, c.treeM.bbox.p, keys, c.actList2.p);
+		radix_sort_pairs(keys, c.actList2.p, c.nActive, 63, c.ws, s);
+		std::swap(c.actList.p, c.actList2.p);
+		std::swap(c.actList.cap, c.actList2.cap);
+	}
+	++c.tileBuilds;
+	c.nTiles = (int)ceil_div(c.nActive, TILE);
+	sa.act = c.actList.p;
+	sa.nActive = c.nActive;
+	SK_LAUNCH(k_tile_build, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles, (float)steps * sa.fStep);
+	if (getenv("SKIDGPU_TILE_DIAG")) {
+		std::vector<int> h(c.nTiles);
+		CK(cudaMemcpyAsync(h.data(), c.tCnt.p, sizeof(int) * c.nTiles, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		long long sum = 0;
+		int over = 0, hist[16] = {0};
+		for (int v : h) {
+			if (v < 0) {
+				++over;
+				continue;
+			}
+			sum += v;
+			int b = v / 128;
+			++hist[b > 15 ? 15 : b];
+		}
+		fprintf(stderr, "tiles: n=%d active=%d steps=%d overflow=%d mean=%.1f hist128:", c.nTiles, c.nActive, steps, over,
+		        c.nTiles > over ? (double)sum / (c.nTiles - over) : 0.0);
+		for (int b = 0; b < 16; ++b) fprintf(stderr, " %d", hist[b]);
+		fprintf(stderr, "\n");
+	}
 }
 
 static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
@@ -624,12 +925,22 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 		launched = 1;
 		sa.act = c.actList.p;
 		sa.nActive = c.nActive;
-		if (use_list_kernel()) {
+		const int mk = move_kernel();
+		if (mk == MOVE_TILE) {
+			if (c.tileStepsLeft <= 0) rebuild_tiles(c, sa, c.tileWindow);
+			--c.tileStepsLeft;
+			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE * 32, 0, c.stream, sa);
+			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, c.stream, sa, sa.queue, 0, sa.queueCount);
+		} else if (mk == MOVE_LIST) {
 			SK_LAUNCH(k_list_eval, (unsigned)ceil_div(c.nActive, EVAL_WARPS), EVAL_WARPS * 32, 0, c.stream, sa);
 			// grid sized for the worst case (everybody refreshes); warps beyond the queue length exit at once
-			SK_LAUNCH(k_list_refresh, (unsigned)ceil_div(c.nActive, REFRESH_WARPS), REFRESH_WARPS * 32, 0, c.stream, sa);
-		} else
-			SK_LAUNCH(k_move_step, (unsigned)ceil_div(c.nActive, STEP_WARPS), STEP_WARPS * 32, 0, c.stream, sa);
+			SK_LAUNCH(k_list_refresh, (unsigned)ceil_div(c.nActive, REFRESH_WARPS), REFRESH_WARPS * 32, 0, c.stream,
+			          sa, sa.queue, sa.queueCount);
+		} else {
+			unsigned g = (unsigned)ceil_div(c.nActive, STEP_WARPS);
+			SK_LAUNCH(k_move_step, g > 148u * 64u ? 148u * 64u : g, STEP_WARPS * 32, 0, c.stream, sa, sa.act,
+			          c.nActive, (const uint32_t *)nullptr);
+		}
 		c.moverSteps += c.nActive;
 	}
 	if (!bNoPrune) sk_reduce(c, c.dT.p + 1, 1, SK_I32, SK_MIN); // fScatDens over all ranks' movers (+inf bits = none)
@@ -663,8 +974,8 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.nMove = (int)nm;
 	c.haveCenters = false;
 	const int m = c.nMove;
-	uint32_t *dT = c.dT.alloc(4);
-	uint32_t initT[3] = {0u, T_NONE, 0u}; // threshold, running min of this step, refresh-queue length
+	uint32_t *dT = c.dT.alloc(8);
+	uint32_t initT[5] = {0u, T_NONE, 0u, 0u, 0u}; // threshold, running min of this step, refresh-queue lengths
 	CK(cudaMemcpyAsync(dT, initT, sizeof initT, cudaMemcpyHostToDevice, s));
 	c.shardLo = (int)((long long)m * c.rank / c.nranks);
 	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
@@ -688,8 +999,17 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.ldelta.alloc(m);
 		c.lhmin.alloc(m);
 		c.lcnt.alloc(m);
-		if (use_list_kernel()) c.mList.alloc((size_t)(c.shardHi - c.shardLo > 0 ? c.shardHi - c.shardLo : 1) * LIST_CAP);
-		c.mQueue.alloc(c.shardHi - c.shardLo > 0 ? c.shardHi - c.shardLo : 1);
+		const int own = c.shardHi - c.shardLo;
+		if (move_kernel() == MOVE_LIST) c.mList.alloc((size_t)(own > 0 ? own : 1) * LIST_CAP);
+		c.mQueue.alloc(own > 0 ? own : 1);
+		if (move_kernel() == MOVE_TILE) {
+			const size_t nt = ceil_div(own > 0 ? own : 1, TILE);
+			c.tList.alloc(nt * TILE_CAP);
+			c.tPos.alloc(nt * TILE);
+			c.tCnt.alloc(nt);
+		}
+		c.tileStepsLeft = 0;
+		c.tileBuilds = 0;
 		SK_LAUNCH(k_init_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeM.perm.p, fileIdx, c.x.p, c.y.p,
 		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p, c.ball2.p, c.lhmin.p, c.lcnt.p, c.listInitFactor);
 		c.actList.alloc(m);
@@ -720,7 +1040,10 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.kernel_ms[0] = 0;
 	c.kernel_launches[0] = 0;
 	kt.start();
+	c.tileWindow = 1; // step 0 is followed by the initial cut and the log line; the blocks of 5 start after it
 	kt.stop(one_step(c, sa, bNoPrune));
+	c.tileStepsLeft = 0;
+	c.tileWindow = 5;
 	if (bInitial && c.nEnt > 0) sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
 	if (bInitial && c.nEnt > 0)
 		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p);
@@ -772,6 +1095,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.nActive = (int)na;
 		std::swap(c.actList.p, c.actList2.p);
 		std::swap(c.actList.cap, c.actList2.cap);
+		c.tileStepsLeft = 0; // the active list changed: new tiles
 		nGlobal = global_active(c.nActive);
 		if (cb) cb(user, 0, nIttr, (int)nGlobal, nScat);
 		++nIttr;
@@ -788,6 +1112,8 @@ void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb,
 	c.nActive = c.shardHi - c.shardLo;
 	if (c.nActive > 0)
 		SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.shardLo, c.nActive, c.actList.p);
+	c.tileStepsLeft = 0;
+	c.tileWindow = nSteps > 0 ? nSteps : 1;
 	StepArgs sa;
 	fill_step_args(c, sa, fStep);
 	for (int i = 0; i < nSteps; ++i) {
