@@ -219,7 +219,10 @@ __device__ __forceinline__ void finish_step(const StepArgs &a, uint32_t id, floa
 		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
 	}
 	if (lane == 0) {
-		if (rmin < 3.0e38f) atomicMin(&a.dT[1], __float_as_uint(rmin)); // smooth1.c:460-461 (rho > 0)
+		// smooth1.c:460-461 (rho > 0).  Millions of atomics on one address serialise in its L2 slice
+		// (~2 clocks each): look first, the running minimum settles after a few thousand movers.
+		if (rmin < 3.0e38f && __float_as_uint(rmin) < *(volatile uint32_t *)&a.dT[1])
+			atomicMin(&a.dT[1], __float_as_uint(rmin));
 		if (a.a0x) {
 			a.a0x[id] = ax;
 			a.a0y[id] = ay;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 10) k_list_eval(const StepArg
 //    (members on both sides of a Morton discontinuity) take the step with their own tree walk
 //    (k_move_step on a queue).
 // Hit set, hit test and pruning rule are those of the reference (and of the v1 kernel).
-constexpr int TILE = 8;       // movers per tile = warps per block
+constexpr int TILE = 8;  // movers per tile = warps per block
 #ifndef TILE_CAP_
 #define TILE_CAP_ 1024
 #endif
