@@ -65,6 +65,8 @@ struct skidgpu_ctx {
 	DevBuf<uint32_t> tList;
 	DevBuf<float4> tPos;
 	DevBuf<int> tCnt;
+	DevBuf<uint32_t> supList;
+	DevBuf<int> supCnt;
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step

@@ -127,6 +127,8 @@ struct StepArgs {
 	uint32_t *tList; // TILE_CAP scatterer indices per tile
 	float4 *tPos;    // per active slot: position at the last rebuild, reach
 	int *tCnt;       // per tile: list length, -1 = overflow (members walk the tree themselves)
+	uint32_t *supList; // SUPER_CAP per supertile (scratch between k_super_walk and k_tile_filter)
+	int *supCnt;
 };
 
 // kdMoveParticles (kd.c:711-729) for one mover.  The reference forms ai = fStep/sqrt(|a|^2) in double and
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 10) k_list_eval(const StepArg
 //  * Every 5 steps (kdPruneInactive's rhythm) the ACTIVE movers are sorted by the Morton key of
 //    their current position and cut into tiles of TILE consecutive movers: compact by construction,
 //    no idle slots as movers freeze.
-//  * k_tile_build (one warp per tile): one tree walk collects every scatterer whose ball comes within
+//  * k_super_walk + k_tile_filter (tile build): per tile, every scatterer whose ball comes within
 //    `reach` of a member, reach = the distance a mover can travel before the next rebuild (a step
 //    moves a mover by exactly fStep, kd.c:716-721).  Until then the list is complete for every
 //    member, so no validity bookkeeping is needed at all.
@@ -351,41 +353,36 @@ __global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t 
 	vals[i] = id;
 }
 
-// one warp per tile: one tree walk collects the union of the members' candidate sets - every scatterer
-// with |x_e - x_m| <= h_e + reach for some member m, reach = the distance a mover can travel before the
-// next rebuild.  Nodes and leaf buckets are pruned against the members themselves (not only against
-// their bounding box): a tile that straddles a Morton discontinuity still gets a short list.
-__global__ void __launch_bounds__(128) k_tile_build(const StepArgs a, int nTiles, float reach)
+// The list of one tile = the union of its members' candidate sets: every scatterer with
+// |x_e - x_m| <= h_e + r for some member m (r = reach + rounding slack).
+// candidate <=> d <= h + r for the nearest member <=> u = d2 - h^2 - r^2 <= 2 h r (no square root, 1e-4 slack)
+#define TILE_MEMBER_TEST(p, cand)                                                                      \
+	{                                                                                              \
+		float d2_ = 3.0e38f;                                                                   \
+		_Pragma("unroll") for (int m = 0; m < TILE; ++m)                                       \
+		{                                                                                      \
+			const float dx = (p).x - mxv[m], dy = (p).y - myv[m], dz = (p).z - mzv[m];     \
+			d2_ = fminf(d2_, dx * dx + dy * dy + dz * dz);                                 \
+		}                                                                                      \
+		const float u_ = d2_ - (p).w - r2;                                                     \
+		cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);                \
+	}
+
+// Slow path of k_tile_build: the tile walks the tree itself; nodes and leaf buckets are pruned against
+// the members (not only their bounding box), so a tile that straddles a Morton discontinuity still gets
+// a short list.  Returns the list length or -1 on overflow.
+__device__ __noinline__ int tile_walk(const StepArgs &a, uint32_t *list, const float (&mxv)[TILE], const float (&myv)[TILE],
+                                      const float (&mzv)[TILE], float r, float T, int lane)
 {
-	const int lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1u;
-	const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
-	if (t >= nTiles) return;
-	const float T = __uint_as_float(a.dT[0]);
-	float mxv[TILE], myv[TILE], mzv[TILE];
+	const float r2 = r * r;
 	float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f, z0 = 3.0e38f, z1 = -3.0e38f;
 #pragma unroll
 	for (int m = 0; m < TILE; ++m) {
-		const int mi = min(t * TILE + m, a.nActive - 1); // a short last tile repeats its last member
-		const uint32_t id = a.act[mi];
-		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
-		x0 = fminf(x0, mxv[m]), x1 = fmaxf(x1, mxv[m]);
-		y0 = fminf(y0, myv[m]), y1 = fmaxf(y1, myv[m]);
-		z0 = fminf(z0, mzv[m]), z1 = fmaxf(z1, mzv[m]);
+		x0 = fminf(x0, mxv[m] - r), x1 = fmaxf(x1, mxv[m] + r);
+		y0 = fminf(y0, myv[m] - r), y1 = fmaxf(y1, myv[m] + r);
+		z0 = fminf(z0, mzv[m] - r), z1 = fmaxf(z1, mzv[m] + r);
 	}
-	// slack for the rounding of the moves and of the tests below
-	const float r = reach * 1.001f + 4.0e-7f * fmaxf(fmaxf(fabsf(x0), fabsf(x1)),
-	                                                 fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(z0), fabsf(z1))));
-	const float r2 = r * r;
-	if (lane < TILE && t * TILE + lane < a.nActive) {
-		float px = mxv[0], py = myv[0], pz = mzv[0];
-#pragma unroll
-		for (int m = 1; m < TILE; ++m)
-			if (lane == m) px = mxv[m], py = myv[m], pz = mzv[m];
-		a.tPos[t * TILE + lane] = make_float4(px, py, pz, r);
-	}
-	x0 -= r, x1 += r, y0 -= r, y1 += r, z0 -= r, z1 += r;
-	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
 	int cnt = 0;
 	bool overflow = false;
 	int lev = a.tv.top - 1;
@@ -406,26 +403,104 @@ __global__ void __launch_bounds__(128) k_tile_build(const StepArgs a, int nTiles
 		const uint32_t m_ = __ballot_sync(SK_FULL, in_);                                       \
 		if (lane == lev) mymask = m_;                                                          \
 	}
-	// candidate <=> d <= h + r for the nearest member <=> u = d2 - h^2 - r^2 <= 2 h r (no square root;
-	// 1e-4 slack); dead scatterers never come back
-#define TILE_LEAF(e_, p)                                                                               \
+	TILE_TEST_CHILDREN();
+	while (!overflow) {
+		uint32_t mk = __shfl_sync(SK_FULL, mymask, lev);
+		if (mk == 0) {
+			++lev;
+			if (lev >= a.tv.top) break;
+			node >>= 5;
+			continue;
+		}
+		const int c = __ffs(mk) - 1;
+		mk &= mk - 1;
+		if (lane == lev) mymask = mk;
+		if (lev > 0) {
+			--lev;
+			node = node * 32 + c;
+			TILE_TEST_CHILDREN();
+			continue;
+		}
+		const uint32_t e = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+		const float4 p = a.entPos[e];
+		bool cand;
+		TILE_MEMBER_TEST(p, cand);
+		if (cand) cand = a.entNR[e].z >= T; // dead scatterers never come back
+		const uint32_t cm = __ballot_sync(SK_FULL, cand);
+		const int nc = __popc(cm);
+		if (cnt + nc > TILE_CAP) overflow = true;
+		else if (cand) list[cnt + __popc(cm & lt)] = e;
+		cnt += nc;
+	}
+#undef TILE_TEST_CHILDREN
+	return overflow ? -1 : cnt;
+}
+
+// Tile lists are built in two kernels.  ncu on the first version (one walk per tile with member tests
+// everywhere, profiles/r01_v4_tilebuild_*): 12 k warp instructions per tile, issue bound.
+//  * k_super_walk (one warp per supertile = SUPER consecutive tiles = 32 consecutive movers of the
+//    sorted active list): ONE walk with cheap bounding-box tests collects the scatterers whose ball
+//    comes within r of the supertile's box - a superset of every member tile's list.
+//  * k_tile_filter (one warp per tile): filters that superset with the exact member test - 4x fewer
+//    tree walks, and the expensive test runs on ~1000 entries instead of ~6000.
+// Supertiles whose superset overflows (members far apart) fall back to tile_walk in k_tile_filter.
+constexpr int SUPER = 32 / TILE;
+constexpr int SUPER_CAP = 2048;
+__global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper, float reach)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1u;
+	const int st = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (st >= nSuper) return;
+	const float T = __uint_as_float(a.dT[0]);
+	const int mi = st * 32 + lane;
+	const uint32_t id = a.act[min(mi, a.nActive - 1)]; // a short last supertile repeats the last mover
+	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+	float x0 = x, x1 = x, y0 = y, y1 = y, z0 = z, z1 = z;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		x0 = fminf(x0, __shfl_xor_sync(SK_FULL, x0, o));
+		x1 = fmaxf(x1, __shfl_xor_sync(SK_FULL, x1, o));
+		y0 = fminf(y0, __shfl_xor_sync(SK_FULL, y0, o));
+		y1 = fmaxf(y1, __shfl_xor_sync(SK_FULL, y1, o));
+		z0 = fminf(z0, __shfl_xor_sync(SK_FULL, z0, o));
+		z1 = fmaxf(z1, __shfl_xor_sync(SK_FULL, z1, o));
+	}
+	// reach = steps until the next rebuild x fStep; slack for the rounding of the moves and of the tests
+	const float r = reach * 1.001f + 4.0e-7f * fmaxf(fmaxf(fabsf(x0), fabsf(x1)),
+	                                                 fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(z0), fabsf(z1))));
+	const float r2 = r * r;
+	if (mi < a.nActive) a.tPos[mi] = make_float4(x, y, z, r);
+	uint32_t *sup = a.supList + (size_t)st * SUPER_CAP;
+	int ns = 0;
+	bool overflow = false;
+	int lev = a.tv.top - 1;
+	uint32_t node = 0, mymask = 0;
+	const float qx0 = x0 - r, qx1 = x1 + r, qy0 = y0 - r, qy1 = y1 + r, qz0 = z0 - r, qz1 = z1 + r;
+#define SUPER_TEST_CHILDREN()                                                                          \
 	{                                                                                              \
-		float d2_ = 3.0e38f;                                                                   \
-		_Pragma("unroll") for (int m = 0; m < TILE; ++m)                                       \
-		{                                                                                      \
-			const float dx = (p).x - mxv[m], dy = (p).y - myv[m], dz = (p).z - mzv[m];     \
-			d2_ = fminf(d2_, dx * dx + dy * dy + dz * dz);                                 \
-		}                                                                                      \
-		const float u_ = d2_ - (p).w - r2;                                                     \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		const float4 lo = bx[0], hi = bx[1];                                                   \
+		const bool in_ = qx1 >= lo.x && qx0 <= hi.x && qy1 >= lo.y && qy0 <= hi.y && qz1 >= lo.z && qz0 <= hi.z && \
+		                 lo.w >= T;                                                            \
+		const uint32_t m_ = __ballot_sync(SK_FULL, in_);                                       \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+	// superset candidate <=> dist(x_e, box) <= h + r (same algebra as the member test)
+#define SUPER_LEAF(e_, p)                                                                              \
+	{                                                                                              \
+		const float gx = fmaxf(fmaxf(x0 - (p).x, (p).x - x1), 0.0f), gy = fmaxf(fmaxf(y0 - (p).y, (p).y - y1), 0.0f), \
+		            gz = fmaxf(fmaxf(z0 - (p).z, (p).z - z1), 0.0f);                           \
+		const float u_ = gx * gx + gy * gy + gz * gz - (p).w - r2;                             \
 		bool cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);           \
-		if (cand) cand = a.entNR[e_].z >= T;                                                   \
+		if (cand) cand = a.entNR[e_].z >= T; /* dead scatterers never come back */             \
 		const uint32_t cm = __ballot_sync(SK_FULL, cand);                                      \
 		const int nc = __popc(cm);                                                             \
-		if (cnt + nc > TILE_CAP) overflow = true;                                              \
-		else if (cand) list[cnt + __popc(cm & lt)] = e_;                                       \
-		cnt += nc;                                                                             \
+		if (ns + nc > SUPER_CAP) overflow = true;                                              \
+		else if (cand) sup[ns + __popc(cm & lt)] = e_;                                         \
+		ns += nc;                                                                              \
 	}
-	TILE_TEST_CHILDREN();
+	SUPER_TEST_CHILDREN();
 	while (!overflow) {
 		uint32_t mk = __shfl_sync(SK_FULL, mymask, lev);
 		if (mk == 0) {
@@ -440,7 +515,7 @@ __global__ void __launch_bounds__(128) k_tile_build(const StepArgs a, int nTiles
 			if (lane == lev) mymask = mk;
 			--lev;
 			node = node * 32 + c;
-			TILE_TEST_CHILDREN();
+			SUPER_TEST_CHILDREN();
 			continue;
 		}
 		// leaf level: two buckets per round so that two record loads are in flight
@@ -452,16 +527,58 @@ __global__ void __launch_bounds__(128) k_tile_build(const StepArgs a, int nTiles
 			const uint32_t e1 = (node * 32 + c1) * 32 + lane;
 			const float4 p1 = a.entPos[e1];
 			if (lane == 0) mymask = mk;
-			TILE_LEAF(e0, p0);
-			TILE_LEAF(e1, p1);
+			SUPER_LEAF(e0, p0);
+			SUPER_LEAF(e1, p1);
 		} else {
 			if (lane == 0) mymask = mk;
-			TILE_LEAF(e0, p0);
+			SUPER_LEAF(e0, p0);
 		}
 	}
-#undef TILE_TEST_CHILDREN
-#undef TILE_LEAF
-	if (lane == 0) a.tCnt[t] = overflow ? -1 : cnt;
+#undef SUPER_TEST_CHILDREN
+#undef SUPER_LEAF
+	if (lane == 0) a.supCnt[st] = overflow ? -1 : ns;
+}
+
+__global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTiles)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t lt = (1u << lane) - 1u;
+	const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (t >= nTiles) return;
+	const float T = __uint_as_float(a.dT[0]);
+	const int st = t / SUPER;
+	const int ns = a.supCnt[st];
+	const uint32_t *sup = a.supList + (size_t)st * SUPER_CAP;
+	uint32_t eN = ns > 0 ? sup[min(lane, ns - 1)] : 0u;
+	float mxv[TILE], myv[TILE], mzv[TILE];
+#pragma unroll
+	for (int m = 0; m < TILE; ++m) {
+		const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
+		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
+	}
+	const float r = a.tPos[t * TILE].w;
+	const float r2 = r * r;
+	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
+	int cnt = 0;
+	if (ns < 0) cnt = tile_walk(a, list, mxv, myv, mzv, r, T, lane);
+	else {
+		bool over = false;
+		for (int s0 = 0; s0 < ns; s0 += 32) {
+			const uint32_t e = eN;
+			const float4 p = a.entPos[e];
+			if (s0 + 32 < ns) eN = sup[min(s0 + 32 + lane, ns - 1)];
+			bool cand;
+			TILE_MEMBER_TEST(p, cand);
+			cand = cand && s0 + lane < ns;
+			const uint32_t cm = __ballot_sync(SK_FULL, cand);
+			const int nc = __popc(cm);
+			if (cnt + nc > TILE_CAP) over = true;
+			else if (cand) list[cnt + __popc(cm & lt)] = e;
+			cnt += nc;
+		}
+		if (over) cnt = -1;
+	}
+	if (lane == 0) a.tCnt[t] = cnt;
 }
 
 constexpr int TILE_CHUNK = 384; // records staged in shared memory at a time
@@ -841,6 +958,8 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tList = c.tList.p;
 	sa.tPos = c.tPos.p;
 	sa.tCnt = c.tCnt.p;
+	sa.supList = c.supList.p;
+	sa.supCnt = c.supCnt.p;
 }
 
 static int count_scatterers(skidgpu_ctx &c)
@@ -898,7 +1017,9 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	c.nTiles = (int)ceil_div(c.nActive, TILE);
 	sa.act = c.actList.p;
 	sa.nActive = c.nActive;
-	SK_LAUNCH(k_tile_build, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles, (float)steps * sa.fStep);
+	const int nSuper = (int)ceil_div(c.nTiles, SUPER);
+	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, (float)steps * sa.fStep);
+	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
 	if (getenv("SKIDGPU_TILE_DIAG")) {
 		std::vector<int> h(c.nTiles);
 		CK(cudaMemcpyAsync(h.data(), c.tCnt.p, sizeof(int) * c.nTiles, cudaMemcpyDeviceToHost, s));
@@ -1010,6 +1131,8 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 			c.tList.alloc(nt * TILE_CAP);
 			c.tPos.alloc(nt * TILE);
 			c.tCnt.alloc(nt);
+			c.supList.alloc(ceil_div(nt, SUPER) * SUPER_CAP);
+			c.supCnt.alloc(ceil_div(nt, SUPER));
 		}
 		c.tileStepsLeft = 0;
 		c.tileBuilds = 0;
