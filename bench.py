@@ -17,8 +17,9 @@ value     = particles / device time of the K timed steps with the snapshot alrea
             (CUDA events on the context's stream, max over ranks).
 e2e       = same metric through the C-ABI with HOST buffers: pinned AoS snapshot -> device inside the
             timed region, labels + catalogue read back every step.
-roofline  = the dominant kernel (gradient walk + move): algorithmic bytes (24*C+24 B per
-            mover-step, C = 85) / its device time measured inside this run.
+roofline  = the dominant kernel (gradient walk + move, k_tile_step, timed together with the tile-list
+            builds and the fallback walk that belong to a step): algorithmic bytes (24*C+24 B
+            per mover-step, C = 85) / device time measured inside this run; one "launch" = one step.
 cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref/skid_ref, serial: 1 core) on
             a bounded sample of the same generator (2^17 particles), timed on this box's host.
 """
@@ -303,9 +304,10 @@ def main():
     peak, peak_src = load_peaks()
     achieved = st["mover_steps"] * BYTES_PER_MOVER_STEP / (st["move_kernel_ms"] * 1e-3) / 1e9 if st["move_kernel_ms"] > 0 else 0.0
     traffic = None
-    try:
+    try:  # ncu dram__bytes_read+write of the step's kernels per mover-step (profiles/roofline_traffic.json)
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get("k_move_step_dram_bytes_per_launch")
+            per = float(json.load(f)["move_dram_bytes_per_mover_step"])
+        traffic = per * st["mover_steps"] / max(st["move_launches"], 1)
     except Exception:
         pass
     out = {
@@ -326,7 +328,7 @@ def main():
                 "d2h_bytes_per_step": int(st_e["d2h"]), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["launches"]),
         "clocks": clocks,
-        "roofline": {"kernel": "k_move_step (gradient walk + move)", "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": "k_tile_step (+ k_super_walk/k_tile_filter list builds and the k_move_step fallback: everything a step launches)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src, "bytes_per_mover_step": BYTES_PER_MOVER_STEP,
                      "mover_steps_per_step": st["mover_steps"] / a.steps,

@@ -67,6 +67,7 @@ struct skidgpu_ctx {
 	DevBuf<int> tCnt;
 	DevBuf<uint32_t> supList;
 	DevBuf<int> supCnt;
+	DevBuf<uint32_t> tileQueue;
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step

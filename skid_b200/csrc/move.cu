@@ -127,6 +127,8 @@ struct StepArgs {
 	uint32_t *tList; // TILE_CAP scatterer indices per tile
 	float4 *tPos;    // per active slot: position at the last rebuild, reach
 	int *tCnt;       // per tile: list length, -1 = overflow (members walk the tree themselves)
+	uint32_t *tileQueue;      // tiles that build their list with their own walk
+	uint32_t *tileQueueCount; // = dT + 3
 	uint32_t *supList; // SUPER_CAP per supertile (scratch between k_super_walk and k_tile_filter)
 	int *supCnt;
 };
@@ -368,14 +370,26 @@ __global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t 
 		cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);                \
 	}
 
-// Slow path of k_tile_build: the tile walks the tree itself; nodes and leaf buckets are pruned against
-// the members (not only their bounding box), so a tile that straddles a Morton discontinuity still gets
-// a short list.  Returns the list length or -1 on overflow.
-__device__ __noinline__ int tile_walk(const StepArgs &a, uint32_t *list, const float (&mxv)[TILE], const float (&myv)[TILE],
-                                      const float (&mzv)[TILE], float r, float T, int lane)
+// Slow path of the tile build (queue filled by k_tile_filter): the tile walks the tree itself; nodes and
+// leaf buckets are pruned against the members (not only their bounding box), so a tile that straddles a
+// Morton discontinuity still gets a short list.
+__global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a)
 {
+	const int lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t nq = *a.tileQueueCount;
+	const float T = __uint_as_float(a.dT[0]);
+	for (uint32_t wi = blockIdx.x * 4 + (threadIdx.x >> 5); wi < nq; wi += gridDim.x * 4) {
+	const int t = (int)a.tileQueue[wi];
+	const float r = a.tPos[t * TILE].w;
 	const float r2 = r * r;
+	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
+	float mxv[TILE], myv[TILE], mzv[TILE];
+#pragma unroll
+	for (int m = 0; m < TILE; ++m) {
+		const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
+		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
+	}
 	float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f, z0 = 3.0e38f, z1 = -3.0e38f;
 #pragma unroll
 	for (int m = 0; m < TILE; ++m) {
@@ -433,7 +447,8 @@ __device__ __noinline__ int tile_walk(const StepArgs &a, uint32_t *list, const f
 		cnt += nc;
 	}
 #undef TILE_TEST_CHILDREN
-	return overflow ? -1 : cnt;
+	if (lane == 0) a.tCnt[t] = overflow ? -1 : cnt;
+	}
 }
 
 // Tile lists are built in two kernels.  ncu on the first version (one walk per tile with member tests
@@ -549,6 +564,11 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	const int st = t / SUPER;
 	const int ns = a.supCnt[st];
 	const uint32_t *sup = a.supList + (size_t)st * SUPER_CAP;
+	const float r = a.tPos[t * TILE].w;
+	if (ns < 0) { // the supertile's members are far apart: own walk (k_tile_walk)
+		if (lane == 0) a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
+		return;
+	}
 	uint32_t eN = ns > 0 ? sup[min(lane, ns - 1)] : 0u;
 	float mxv[TILE], myv[TILE], mzv[TILE];
 #pragma unroll
@@ -556,12 +576,10 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 		const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
 		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
 	}
-	const float r = a.tPos[t * TILE].w;
 	const float r2 = r * r;
 	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
 	int cnt = 0;
-	if (ns < 0) cnt = tile_walk(a, list, mxv, myv, mzv, r, T, lane);
-	else {
+	{
 		bool over = false;
 		for (int s0 = 0; s0 < ns; s0 += 32) {
 			const uint32_t e = eN;
@@ -959,6 +977,8 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tPos = c.tPos.p;
 	sa.tCnt = c.tCnt.p;
 	sa.supList = c.supList.p;
+	sa.tileQueue = c.tileQueue.p;
+	sa.tileQueueCount = c.dT.p ? c.dT.p + 3 : nullptr;
 	sa.supCnt = c.supCnt.p;
 }
 
@@ -1020,6 +1040,7 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	const int nSuper = (int)ceil_div(c.nTiles, SUPER);
 	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, (float)steps * sa.fStep);
 	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
+	SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, s, sa);
 	if (getenv("SKIDGPU_TILE_DIAG")) {
 		std::vector<int> h(c.nTiles);
 		CK(cudaMemcpyAsync(h.data(), c.tCnt.p, sizeof(int) * c.nTiles, cudaMemcpyDeviceToHost, s));
@@ -1039,6 +1060,16 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 		        c.nTiles > over ? (double)sum / (c.nTiles - over) : 0.0);
 		for (int b = 0; b < 16; ++b) fprintf(stderr, " %d", hist[b]);
 		fprintf(stderr, "\n");
+		std::vector<int> hs(nSuper);
+		CK(cudaMemcpyAsync(hs.data(), c.supCnt.p, sizeof(int) * nSuper, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		long long ssum = 0;
+		int sover = 0;
+		for (int v : hs) {
+			if (v < 0) ++sover;
+			else ssum += v;
+		}
+		fprintf(stderr, "supertiles: n=%d overflow=%d mean=%.1f\n", nSuper, sover, nSuper > sover ? (double)ssum / (nSuper - sover) : 0.0);
 	}
 }
 
@@ -1133,6 +1164,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 			c.tCnt.alloc(nt);
 			c.supList.alloc(ceil_div(nt, SUPER) * SUPER_CAP);
 			c.supCnt.alloc(ceil_div(nt, SUPER));
+			c.tileQueue.alloc(nt);
 		}
 		c.tileStepsLeft = 0;
 		c.tileBuilds = 0;

@@ -79,8 +79,10 @@ def make_box(n, seed=1234, kind="dark", sigma_frac=0.45):
     vel = vel[perm].astype(np.float32)
     pos[pos <= -0.5] = 0.5
     pos[pos > 0.5] = 0.5
-    # no duplicate positions (the reference divides by fBall2 / r: SIGFPE, main.c:76)
-    for _ in range(8):
+    # no duplicate positions (the reference divides by fBall2 / r: SIGFPE, main.c:76).  The check sorts
+    # all positions; above 2^22 particles it is skipped (a stray duplicate pair is harmless for both
+    # codes - only >= nSmooth coincident particles make fBall2 zero - and the sort costs minutes at 2^27)
+    for _ in range(8 if n <= (1 << 22) else 0):
         key = np.ascontiguousarray(pos).view([("", np.float32)] * 3).ravel()
         _, first = np.unique(key, return_index=True)
         if len(first) == n:
