@@ -302,12 +302,14 @@ def main():
     value = total_particles * a.steps / (ms_dev * 1e-3)
     e2e_value = total_particles * a.steps / (ms_e2e * 1e-3)
     peak, peak_src = load_peaks()
-    achieved = st["mover_steps"] * BYTES_PER_MOVER_STEP / (st["move_kernel_ms"] * 1e-3) / 1e9 if st["move_kernel_ms"] > 0 else 0.0
+    # per GPU: the mover-steps of all shards / N over the slowest shard's kernel time, against ONE GPU's peak
+    per_gpu_steps = st["mover_steps"] / (world if shard else 1)
+    achieved = per_gpu_steps * BYTES_PER_MOVER_STEP / (st["move_kernel_ms"] * 1e-3) / 1e9 if st["move_kernel_ms"] > 0 else 0.0
     traffic = None
     try:  # ncu dram__bytes_read+write of the step's kernels per mover-step (profiles/roofline_traffic.json)
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             per = float(json.load(f)["move_dram_bytes_per_mover_step"])
-        traffic = per * st["mover_steps"] / max(st["move_launches"], 1)
+        traffic = per * per_gpu_steps / max(st["move_launches"], 1)
     except Exception:
         pass
     out = {
