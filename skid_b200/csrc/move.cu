@@ -210,8 +210,24 @@ constexpr int LIST_CAP = 384;
 constexpr int EVAL_WARPS = 4;
 constexpr int REFRESH_WARPS = 4;
 
-// the end of every step for one mover: min density of the scatterers that hit it, optional copy of
-// the acceleration, kdMoveParticles
+// the end of every step for one mover (one thread): min density of the scatterers that hit it, optional
+// copy of the acceleration, kdMoveParticles
+__device__ __forceinline__ void finish_mover(const StepArgs &a, uint32_t id, float x, float y, float z, float ax,
+                                             float ay, float az, float rmin)
+{
+	// smooth1.c:460-461 (rho > 0).  Millions of atomics on one address serialise in its L2 slice
+	// (~2 clocks each): look first, the running minimum settles after a few thousand movers.
+	if (rmin < 3.0e38f && __float_as_uint(rmin) < *(volatile uint32_t *)&a.dT[1])
+		atomicMin(&a.dT[1], __float_as_uint(rmin));
+	if (a.a0x) {
+		a.a0x[id] = ax;
+		a.a0y[id] = ay;
+		a.a0z[id] = az;
+	}
+	move_one(a, id, x, y, z, ax, ay, az);
+}
+
+// warp-wide version: one warp per mover, partial sums in the 32 lanes
 __device__ __forceinline__ void finish_step(const StepArgs &a, uint32_t id, float x, float y, float z, float ax,
                                             float ay, float az, float rmin, int lane)
 {
@@ -222,18 +238,7 @@ __device__ __forceinline__ void finish_step(const StepArgs &a, uint32_t id, floa
 		az += __shfl_xor_sync(SK_FULL, az, o);
 		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
 	}
-	if (lane == 0) {
-		// smooth1.c:460-461 (rho > 0).  Millions of atomics on one address serialise in its L2 slice
-		// (~2 clocks each): look first, the running minimum settles after a few thousand movers.
-		if (rmin < 3.0e38f && __float_as_uint(rmin) < *(volatile uint32_t *)&a.dT[1])
-			atomicMin(&a.dT[1], __float_as_uint(rmin));
-		if (a.a0x) {
-			a.a0x[id] = ax;
-			a.a0y[id] = ay;
-			a.a0z[id] = az;
-		}
-		move_one(a, id, x, y, z, ax, ay, az);
-	}
+	if (lane == 0) finish_mover(a, id, x, y, z, ax, ay, az, rmin);
 }
 
 // One list entry: the reference's float32 hit test (smBallGather, smooth1.c:365-369: dx = x_scatterer -
@@ -599,20 +604,28 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	if (lane == 0) a.tCnt[t] = cnt;
 }
 
-constexpr int TILE_CHUNK = 384; // records staged in shared memory at a time
+// ncu on the first k_tile_step (one warp per mover, profiles/r01_v5_tilestep_*): issue bound at 606
+// warp instructions per mover-step, of which only ~310 are hit tests and spline terms - the rest is
+// per-warp overhead (prologue, staging loop, 5-stage reductions of 4 values, the move itself).  The
+// pair tests per tile are fixed (members x list length), so LPM lanes per mover instead of 32 keep the
+// lane work unchanged and divide the per-warp overhead by 32/LPM: one block of TILE*LPM threads per
+// tile, 32/LPM movers per warp.
+constexpr int TILE_CHUNK = 256; // records staged in shared memory at a time
+constexpr int LPM = 8;          // lanes per mover
+constexpr int TILE_THREADS = TILE * LPM;
 struct TileShared {
 	float4 p[TILE_CHUNK]; // (x,y,z,fBall2 or -1 when dead)
 	float4 q[TILE_CHUNK]; // (4/fBall2, fNorm, rho, 0)
 };
 
-__global__ void __launch_bounds__(TILE * 32, 8) k_tile_step(const StepArgs a)
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
 {
 	__shared__ TileShared sh;
 	__shared__ uint32_t sh_e[TILE_CHUNK];
-	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
 	const int t = blockIdx.x;
 	const int cnt = a.tCnt[t];
-	const int mi = t * TILE + w;
+	const int mi = t * TILE + m;
 	const bool have = mi < a.nActive;
 	const uint32_t id = have ? a.act[mi] : 0u;
 	float x = 0.0f, y = 0.0f, z = 0.0f;
@@ -624,9 +637,7 @@ __global__ void __launch_bounds__(TILE * 32, 8) k_tile_step(const StepArgs a)
 		const float ox = x - b.x, oy = y - b.y, oz = z - b.z;
 		inside = ox * ox + oy * oy + oz * oz <= b.w * b.w;
 	}
-	if (have && !inside) { // overflowed tile, or the mover left its ball: own tree walk
-		if (lane == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id;
-	}
+	if (have && !inside && j == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id; // overflowed tile, or left its ball: own walk
 	const bool run = have && inside;
 	const uint32_t *list = a.tList + (size_t)t * TILE_CAP;
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
@@ -634,7 +645,7 @@ __global__ void __launch_bounds__(TILE * 32, 8) k_tile_step(const StepArgs a)
 	for (int c0 = 0; c0 < cnt; c0 += TILE_CHUNK) {
 		const int nc = min(cnt - c0, TILE_CHUNK);
 		if (c0) __syncthreads();
-		for (int s = threadIdx.x; s < nc; s += TILE * 32) {
+		for (int s = threadIdx.x; s < nc; s += TILE_THREADS) {
 			const uint32_t e = list[c0 + s];
 			float4 p = a.entRec[2 * (size_t)e];
 			const float4 q = a.entRec[2 * (size_t)e + 1];
@@ -645,7 +656,7 @@ __global__ void __launch_bounds__(TILE * 32, 8) k_tile_step(const StepArgs a)
 		}
 		__syncthreads();
 		if (run) {
-			for (int s = lane; s < nc; s += 32) {
+			for (int s = j; s < nc; s += LPM) {
 				const float4 p = sh.p[s];
 				// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
 				const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
@@ -658,7 +669,14 @@ __global__ void __launch_bounds__(TILE * 32, 8) k_tile_step(const StepArgs a)
 			}
 		}
 	}
-	if (run) finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
+#pragma unroll
+	for (int o = LPM / 2; o > 0; o >>= 1) {
+		ax += __shfl_xor_sync(SK_FULL, ax, o);
+		ay += __shfl_xor_sync(SK_FULL, ay, o);
+		az += __shfl_xor_sync(SK_FULL, az, o);
+		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
+	}
+	if (run && j == 0) finish_mover(a, id, x, y, z, ax, ay, az, rmin);
 }
 
 // v1 kernel: one warp per mover walks the scatterer tree every step (profiles/r01_v1_move_*: issue
@@ -1084,7 +1102,7 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 		if (mk == MOVE_TILE) {
 			if (c.tileStepsLeft <= 0) rebuild_tiles(c, sa, c.tileWindow);
 			--c.tileStepsLeft;
-			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE * 32, 0, c.stream, sa);
+			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa);
 			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, c.stream, sa, sa.queue, 0, sa.queueCount);
 		} else if (mk == MOVE_LIST) {
 			SK_LAUNCH(k_list_eval, (unsigned)ceil_div(c.nActive, EVAL_WARPS), EVAL_WARPS * 32, 0, c.stream, sa);
