@@ -62,12 +62,14 @@ struct skidgpu_ctx {
 	// tiles: TILE consecutive entries of the position-sorted active list share one scatterer list (move.cu)
 	int nTiles = 0, tileStepsLeft = 0, tileWindow = 5, tileBuilds = 0;
 	DevBuf<uint64_t> tKeys;
-	DevBuf<uint32_t> tList;
+	DevBuf<uint32_t> tList, tOff;
+	uint32_t bigBase = 0, nBig = 0;
 	DevBuf<float4> tPos;
 	DevBuf<int> tCnt;
 	DevBuf<uint32_t> supList;
 	DevBuf<int> supCnt;
-	DevBuf<uint32_t> tileQueue;
+	DevBuf<uint32_t> tileQueue, shortQueue;
+	bool tileFresh = false;
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step

@@ -124,7 +124,10 @@ struct StepArgs {
 	uint32_t *queueCount; // = dT + 2, reset by k_update_T
 	float wrapHiF[3], wrapLoF[3]; // largest floats <= wrapHi / wrapLo: same decisions as the double compares
 	// tiles (k_tile_build / k_tile_step): TILE consecutive entries of the position-sorted active list
-	uint32_t *tList; // TILE_CAP scatterer indices per tile
+	uint32_t *tList; // nTiles small slots (TILE_CAP), then nBig big slots (BIG_CAP) from bigBase
+	uint32_t *tOff;  // per tile: where its list starts
+	uint32_t bigBase, nBig;
+	uint32_t *bigCount; // = dT + 6
 	float4 *tPos;    // per active slot: position at the last rebuild, reach
 	int *tCnt;       // per tile: list length, -1 = overflow (members walk the tree themselves)
 	uint32_t *tileQueue;      // tiles that build their list with their own walk
@@ -318,15 +321,41 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 10) k_list_eval(const StepArg
 //  * k_tile_step (one block per tile, one warp per mover, every step): the tile's records are fetched
 //    ONCE (TILE x fewer scattered fetches per mover-step) into shared memory, then every warp runs
 //    the reference's float32 hit test for its mover against the staged records.
-//  * Movers that leave their ball (a periodic wrap moves them by L) and tiles whose list overflows TILE_CAP
+//  * Movers that leave their ball (a periodic wrap moves them by L) and tiles whose list overflows even a big slot
 //    (members on both sides of a Morton discontinuity) take the step with their own tree walk
 //    (k_move_step on a queue).
 // Hit set, hit test and pruning rule are those of the reference (and of the v1 kernel).
 constexpr int TILE = 8;  // movers per tile = warps per block
-#ifndef TILE_CAP_
-#define TILE_CAP_ 1024
-#endif
-constexpr int TILE_CAP = TILE_CAP_; // scatterers per tile list
+constexpr int TILE_CAP = 512;  // scatterers per tile list (every tile owns a slot of this size)
+constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take a big slot from a pool
+
+// Append the lanes with `cand` to the tile's list (warp-wide, order preserving).  A list that outgrows its
+// small slot moves to a big slot of the pool; one that outgrows that too (or finds the pool empty) overflows.
+#define TILE_APPEND(cand, e_)                                                                          \
+	{                                                                                              \
+		const uint32_t cm_ = __ballot_sync(SK_FULL, cand);                                     \
+		const int nc_ = __popc(cm_);                                                           \
+		if (cnt + nc_ > cap) {                                                                 \
+			uint32_t slot_ = 0xffffffffu;                                                  \
+			if (cap == TILE_CAP) {                                                         \
+				if (lane == 0) slot_ = atomicAdd(a.bigCount, 1u);                      \
+				slot_ = __shfl_sync(SK_FULL, slot_, 0);                                \
+			}                                                                              \
+			if (slot_ < a.nBig) {                                                          \
+				const uint32_t noff_ = a.bigBase + slot_ * (uint32_t)BIG_CAP;          \
+				uint32_t *nl_ = a.tList + noff_;                                       \
+				__syncwarp();                                                          \
+				for (int i_ = lane; i_ < cnt; i_ += 32) nl_[i_] = list[i_];            \
+				list = nl_;                                                            \
+				off = noff_;                                                           \
+				cap = BIG_CAP;                                                         \
+			} else overflow = true;                                                        \
+		}                                                                                      \
+		if (!overflow) {                                                                       \
+			if (cand) list[cnt + __popc(cm_ & lt)] = e_;                                   \
+			cnt += nc_;                                                                    \
+		}                                                                                      \
+	}
 constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
@@ -375,37 +404,53 @@ __global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t 
 		cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);                \
 	}
 
-// Slow path of the tile build (queue filled by k_tile_filter): the tile walks the tree itself; nodes and
-// leaf buckets are pruned against the members (not only their bounding box), so a tile that straddles a
-// Morton discontinuity still gets a short list.
-__global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a)
+// Slow path of the tile build: the tiles in `queue` walk the tree themselves; nodes and leaf buckets are
+// pruned against the members (not only their bounding box), so a tile that straddles a Morton
+// discontinuity still gets a short list.
+// Short tiles: in the cores of dense clumps the ball radii are smaller than the 5-step reach and the
+// list explodes ((h + 5 fStep)^3 / h^3).  A tile whose list overflows with `reach` is rebuilt with
+// `reachShort` (one step) and appended to `shortQueue`: it is then walked again before EVERY step of
+// the window (one_step launches this kernel on the short queue with reach = 0).
+__global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a, const uint32_t *queue, const uint32_t *queueCount,
+                                                   float reach, float reachShort, uint32_t *shortQueue,
+                                                   uint32_t *shortCount)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1u;
-	const uint32_t nq = *a.tileQueueCount;
+	const uint32_t nq = *queueCount;
 	const float T = __uint_as_float(a.dT[0]);
 	for (uint32_t wi = blockIdx.x * 4 + (threadIdx.x >> 5); wi < nq; wi += gridDim.x * 4) {
-	const int t = (int)a.tileQueue[wi];
-	const float r = a.tPos[t * TILE].w;
-	const float r2 = r * r;
-	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
-	float mxv[TILE], myv[TILE], mzv[TILE];
+		const int t = (int)queue[wi];
+		uint32_t off = (uint32_t)t * TILE_CAP;
+		uint32_t *list = a.tList + off;
+		int cap = TILE_CAP;
+		float mxv[TILE], myv[TILE], mzv[TILE];
+		float amax = 0.0f;
 #pragma unroll
-	for (int m = 0; m < TILE; ++m) {
-		const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
-		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
-	}
-	float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f, z0 = 3.0e38f, z1 = -3.0e38f;
+		for (int m = 0; m < TILE; ++m) {
+			const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
+			mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
+			amax = fmaxf(amax, fmaxf(fabsf(mxv[m]), fmaxf(fabsf(myv[m]), fabsf(mzv[m]))));
+		}
+		int cnt = 0;
+		bool overflow = true;
+		float r = 0.0f;
+		for (int attempt = 0; attempt < 2 && overflow; ++attempt) {
+			const float rr = attempt == 0 ? reach : reachShort;
+			if (!(rr > 0.0f)) continue;
+			r = rr * 1.001f + 4.0e-7f * amax; // slack for the rounding of the moves and of the tests
+			const float r2 = r * r;
+			float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f, z0 = 3.0e38f, z1 = -3.0e38f;
 #pragma unroll
-	for (int m = 0; m < TILE; ++m) {
-		x0 = fminf(x0, mxv[m] - r), x1 = fmaxf(x1, mxv[m] + r);
-		y0 = fminf(y0, myv[m] - r), y1 = fmaxf(y1, myv[m] + r);
-		z0 = fminf(z0, mzv[m] - r), z1 = fmaxf(z1, mzv[m] + r);
-	}
-	int cnt = 0;
-	bool overflow = false;
-	int lev = a.tv.top - 1;
-	uint32_t node = 0, mymask = 0;
+			for (int m = 0; m < TILE; ++m) {
+				x0 = fminf(x0, mxv[m] - r), x1 = fmaxf(x1, mxv[m] + r);
+				y0 = fminf(y0, myv[m] - r), y1 = fmaxf(y1, myv[m] + r);
+				z0 = fminf(z0, mzv[m] - r), z1 = fmaxf(z1, mzv[m] + r);
+			}
+			cnt = 0;
+			overflow = false;
+			int lev = a.tv.top - 1;
+			uint32_t node = 0, mymask = 0;
 #define TILE_TEST_CHILDREN()                                                                           \
 	{                                                                                              \
 		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
@@ -422,37 +467,45 @@ __global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a)
 		const uint32_t m_ = __ballot_sync(SK_FULL, in_);                                       \
 		if (lane == lev) mymask = m_;                                                          \
 	}
-	TILE_TEST_CHILDREN();
-	while (!overflow) {
-		uint32_t mk = __shfl_sync(SK_FULL, mymask, lev);
-		if (mk == 0) {
-			++lev;
-			if (lev >= a.tv.top) break;
-			node >>= 5;
-			continue;
-		}
-		const int c = __ffs(mk) - 1;
-		mk &= mk - 1;
-		if (lane == lev) mymask = mk;
-		if (lev > 0) {
-			--lev;
-			node = node * 32 + c;
 			TILE_TEST_CHILDREN();
-			continue;
-		}
-		const uint32_t e = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
-		const float4 p = a.entPos[e];
-		bool cand;
-		TILE_MEMBER_TEST(p, cand);
-		if (cand) cand = a.entNR[e].z >= T; // dead scatterers never come back
-		const uint32_t cm = __ballot_sync(SK_FULL, cand);
-		const int nc = __popc(cm);
-		if (cnt + nc > TILE_CAP) overflow = true;
-		else if (cand) list[cnt + __popc(cm & lt)] = e;
-		cnt += nc;
-	}
+			while (!overflow) {
+				uint32_t mk = __shfl_sync(SK_FULL, mymask, lev);
+				if (mk == 0) {
+					++lev;
+					if (lev >= a.tv.top) break;
+					node >>= 5;
+					continue;
+				}
+				const int c = __ffs(mk) - 1;
+				mk &= mk - 1;
+				if (lane == lev) mymask = mk;
+				if (lev > 0) {
+					--lev;
+					node = node * 32 + c;
+					TILE_TEST_CHILDREN();
+					continue;
+				}
+				const uint32_t e = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+				const float4 p = a.entPos[e];
+				bool cand;
+				TILE_MEMBER_TEST(p, cand);
+				if (cand) cand = a.entNR[e].z >= T; // dead scatterers never come back
+				TILE_APPEND(cand, e);
+			}
 #undef TILE_TEST_CHILDREN
-	if (lane == 0) a.tCnt[t] = overflow ? -1 : cnt;
+			if (!overflow && attempt == 1 && shortQueue && lane == 0) shortQueue[atomicAdd(shortCount, 1u)] = (uint32_t)t;
+		}
+		if (!overflow && lane < TILE && t * TILE + lane < a.nActive) { // where the list was built and how far it reaches
+			float px = mxv[0], py = myv[0], pz = mzv[0];
+#pragma unroll
+			for (int m = 1; m < TILE; ++m)
+				if (lane == m) px = mxv[m], py = myv[m], pz = mzv[m];
+			a.tPos[t * TILE + lane] = make_float4(px, py, pz, r);
+		}
+		if (lane == 0) {
+			a.tCnt[t] = overflow ? -1 : cnt;
+			a.tOff[t] = off;
+		}
 	}
 }
 
@@ -582,26 +635,30 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
 	}
 	const float r2 = r * r;
-	uint32_t *list = a.tList + (size_t)t * TILE_CAP;
+	uint32_t off = (uint32_t)t * TILE_CAP;
+	uint32_t *list = a.tList + off;
+	int cap = TILE_CAP;
 	int cnt = 0;
 	{
-		bool over = false;
-		for (int s0 = 0; s0 < ns; s0 += 32) {
+		bool overflow = false;
+		for (int s0 = 0; s0 < ns && !overflow; s0 += 32) {
 			const uint32_t e = eN;
 			const float4 p = a.entPos[e];
 			if (s0 + 32 < ns) eN = sup[min(s0 + 32 + lane, ns - 1)];
 			bool cand;
 			TILE_MEMBER_TEST(p, cand);
 			cand = cand && s0 + lane < ns;
-			const uint32_t cm = __ballot_sync(SK_FULL, cand);
-			const int nc = __popc(cm);
-			if (cnt + nc > TILE_CAP) over = true;
-			else if (cand) list[cnt + __popc(cm & lt)] = e;
-			cnt += nc;
+			TILE_APPEND(cand, e);
 		}
-		if (over) cnt = -1;
+		if (overflow) { // too long for the 5-step reach: k_tile_walk retries and falls back to a one-step list
+			if (lane == 0) a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
+			return;
+		}
 	}
-	if (lane == 0) a.tCnt[t] = cnt;
+	if (lane == 0) {
+		a.tCnt[t] = cnt;
+		a.tOff[t] = off;
+	}
 }
 
 // ncu on the first k_tile_step (one warp per mover, profiles/r01_v5_tilestep_*): issue bound at 606
@@ -639,7 +696,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
 	}
 	if (have && !inside && j == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id; // overflowed tile, or left its ball: own walk
 	const bool run = have && inside;
-	const uint32_t *list = a.tList + (size_t)t * TILE_CAP;
+	const uint32_t *list = a.tList + a.tOff[t];
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
 	float rmin = 3.0e38f;
 	for (int c0 = 0; c0 < cnt; c0 += TILE_CHUNK) {
@@ -992,6 +1049,10 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 		sa.wrapLoF[d] = l;
 	}
 	sa.tList = c.tList.p;
+	sa.tOff = c.tOff.p;
+	sa.bigBase = c.bigBase;
+	sa.nBig = c.nBig;
+	sa.bigCount = c.dT.p ? c.dT.p + 6 : nullptr;
 	sa.tPos = c.tPos.p;
 	sa.tCnt = c.tCnt.p;
 	sa.supList = c.supList.p;
@@ -1056,9 +1117,13 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	sa.act = c.actList.p;
 	sa.nActive = c.nActive;
 	const int nSuper = (int)ceil_div(c.nTiles, SUPER);
+	CK(cudaMemsetAsync(c.dT.p + 5, 0, 2 * sizeof(uint32_t), s)); // short-tile queue, big slots in use
 	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, (float)steps * sa.fStep);
 	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
-	SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, s, sa);
+	// spread-out supertiles build per tile; tiles whose 5-step list overflows become short tiles (dT[5])
+	SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, s, sa, sa.tileQueue, sa.tileQueueCount, (float)steps * sa.fStep,
+	          steps > 1 ? sa.fStep : 0.0f, c.shortQueue.p, c.dT.p + 5);
+	c.tileFresh = true;
 	if (getenv("SKIDGPU_TILE_DIAG")) {
 		std::vector<int> h(c.nTiles);
 		CK(cudaMemcpyAsync(h.data(), c.tCnt.p, sizeof(int) * c.nTiles, cudaMemcpyDeviceToHost, s));
@@ -1102,6 +1167,10 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 		if (mk == MOVE_TILE) {
 			if (c.tileStepsLeft <= 0) rebuild_tiles(c, sa, c.tileWindow);
 			--c.tileStepsLeft;
+			if (!c.tileFresh) // short tiles are rebuilt before every step (their list reaches one step)
+				SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, c.stream, sa, c.shortQueue.p, c.dT.p + 5, 0.0f, sa.fStep,
+				          (uint32_t *)nullptr, (uint32_t *)nullptr);
+			c.tileFresh = false;
 			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa);
 			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, c.stream, sa, sa.queue, 0, sa.queueCount);
 		} else if (mk == MOVE_LIST) {
@@ -1148,7 +1217,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.haveCenters = false;
 	const int m = c.nMove;
 	uint32_t *dT = c.dT.alloc(8);
-	uint32_t initT[5] = {0u, T_NONE, 0u, 0u, 0u}; // threshold, running min of this step, refresh-queue lengths
+	uint32_t initT[7] = {0u, T_NONE, 0u, 0u, 0u, 0u, 0u}; // threshold, running min of this step, refresh-queue lengths
 	CK(cudaMemcpyAsync(dT, initT, sizeof initT, cudaMemcpyHostToDevice, s));
 	c.shardLo = (int)((long long)m * c.rank / c.nranks);
 	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
@@ -1177,12 +1246,16 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.mQueue.alloc(own > 0 ? own : 1);
 		if (move_kernel() == MOVE_TILE) {
 			const size_t nt = ceil_div(own > 0 ? own : 1, TILE);
-			c.tList.alloc(nt * TILE_CAP);
+			c.bigBase = (uint32_t)(nt * TILE_CAP);
+			c.nBig = (uint32_t)(nt / 8 + 1024);
+			c.tList.alloc(nt * TILE_CAP + (size_t)c.nBig * BIG_CAP);
+			c.tOff.alloc(nt);
 			c.tPos.alloc(nt * TILE);
 			c.tCnt.alloc(nt);
 			c.supList.alloc(ceil_div(nt, SUPER) * SUPER_CAP);
 			c.supCnt.alloc(ceil_div(nt, SUPER));
 			c.tileQueue.alloc(nt);
+			c.shortQueue.alloc(nt);
 		}
 		c.tileStepsLeft = 0;
 		c.tileBuilds = 0;
