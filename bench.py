@@ -117,6 +117,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"], help="multi-GPU layout (N>1)")
     a = ap.parse_args()
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"  # keep stdout to the one JSON line (NCCL prints its version banner there)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -341,6 +343,7 @@ def main():
     if shard:
         out["config"]["particles_total"] = n
         out["config"]["nccl_bytes_per_step"] = reducer.bytes // max(1, (W + a.steps + 1 + a.steps))
+        out["config"]["reduce_callback_host_ms_per_step"] = 1e3 * reducer.host_s / max(1, (W + a.steps + 1 + a.steps))
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             v, info = run_reference_sample(a.kind, a.cpu_log2n, seed=7)

@@ -99,10 +99,14 @@ int skidgpu_set_soft(skidgpu_ctx *ctx, float fEps);
 typedef int (*skidgpu_reduce_cb)(void *user, void *dev, long long count, int dtype, int op);
 int skidgpu_set_reduce_cb(skidgpu_ctx *ctx, skidgpu_reduce_cb cb, void *user);
 
-/* Device arrays x,y,z (nMove floats each) of the current mover positions and the [lo,hi) range of
- * movers this shard owns; the caller all-gathers the owned ranges before skidgpu_fof and
- * skidgpu_centers (positions of movers owned by other ranks are stale otherwise). */
+/* Device arrays x,y,z (nMove floats each) of the current mover positions.  Movers are owned
+ * block-cyclically (blocks of 256 consecutive movers of the Morton-ordered list, block j -> rank
+ * j % nranks; [lo,hi) is only meaningful for the contiguous layout of SKIDGPU_MOVE_KERNEL=list).
+ * Before skidgpu_fof and skidgpu_centers the caller exchanges positions: skidgpu_mask_unowned_movers
+ * zeroes the entries other ranks own, then one all-reduce(sum) per array makes every rank hold
+ * every mover (positions of movers owned by other ranks are stale otherwise). */
 int skidgpu_mover_arrays(skidgpu_ctx *ctx, float **dx, float **dy, float **dz, int *nMove, int *lo, int *hi);
+int skidgpu_mask_unowned_movers(skidgpu_ctx *ctx);
 
 /* kdScatterActive + kdBuildTree + smInit + smDensityInit (main.c:374-378):
  * tree over the scatter-active species, exact periodic k-nearest (k = nSmooth, self

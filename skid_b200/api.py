@@ -32,7 +32,7 @@ EXPORTS = [
     "skidgpu_get_neighbors", "skidgpu_move", "skidgpu_keep_step0", "skidgpu_get_step0", "skidgpu_fof",
     "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_moved_dev", "skidgpu_centers", "skidgpu_set_groups",
     "skidgpu_unbind", "skidgpu_stage_ms", "skidgpu_counter", "skidgpu_debug_sort", "skidgpu_debug_scan",
-    "skidgpu_kernel_ms", "skidgpu_stream", "skidgpu_set_reduce_cb", "skidgpu_mover_arrays",
+    "skidgpu_kernel_ms", "skidgpu_stream", "skidgpu_set_reduce_cb", "skidgpu_mover_arrays", "skidgpu_mask_unowned_movers",
 ]
 
 
@@ -78,6 +78,7 @@ def load_library():
     lib.skidgpu_stream.restype = vp
     lib.skidgpu_set_reduce_cb.argtypes = [vp, vp, vp]
     lib.skidgpu_mover_arrays.argtypes = [vp, P(vp), P(vp), P(vp), P(i), P(i), P(i)]
+    lib.skidgpu_mask_unowned_movers.argtypes = [vp]
     lib.skidgpu_debug_sort.argtypes = [vp, vp, vp, C.c_longlong, i]
     lib.skidgpu_debug_scan.argtypes = [vp, vp, vp, C.c_longlong]
     _lib = lib
@@ -159,6 +160,10 @@ class SkidGPU:
         self._ck(self.lib.skidgpu_mover_arrays(self.h, C.byref(px), C.byref(py), C.byref(pz), C.byref(nm),
                                                C.byref(lo), C.byref(hi)))
         return px.value, py.value, pz.value, nm.value, lo.value, hi.value
+
+    def mask_unowned_movers(self):
+        """Zero the positions of movers other ranks own (then all-reduce(sum) the arrays)."""
+        self._ck(self.lib.skidgpu_mask_unowned_movers(self.h))
 
     def kdSetSoft(self, fEps):
         self._ck(self.lib.skidgpu_set_soft(self.h, fEps))

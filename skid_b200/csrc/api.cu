@@ -368,6 +368,14 @@ extern "C" int skidgpu_set_reduce_cb(skidgpu_ctx *ctx, skidgpu_reduce_cb cb, voi
 	API_END(ctx)
 }
 
+extern "C" int skidgpu_mask_unowned_movers(skidgpu_ctx *ctx)
+{
+	API_BEGIN(ctx)
+	move_mask_unowned(*ctx);
+	CK(cudaStreamSynchronize(ctx->stream));
+	API_END(ctx)
+}
+
 extern "C" int skidgpu_mover_arrays(skidgpu_ctx *ctx, float **dx, float **dy, float **dz, int *nMove, int *lo, int *hi)
 {
 	API_BEGIN(ctx)

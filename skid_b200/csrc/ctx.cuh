@@ -78,6 +78,8 @@ struct skidgpu_ctx {
 	DevBuf<float> a0x, a0y, a0z;
 	DevBuf<uint8_t> aliveByOrd;
 	int shardLo = 0, shardHi = 0;
+	bool cyclic = false; // movers owned block-cyclically (move.cu) instead of [shardLo, shardHi)
+	int nOwned = 0;
 	DevBuf<float> mxyz; // contiguous x|y|z copy for the multi-GPU exchange
 
 	// ---- groups
@@ -145,6 +147,7 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
                 int bForceInitialCut, int bNoPrune, skidgpu_log_cb cb, void *user, int *nMove, int *nIttr);
 void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb, void *user);
+void move_mask_unowned(skidgpu_ctx &c); // zero the positions of movers other ranks own (before the sum-exchange)
 void stage_fof(skidgpu_ctx &c, float fTau, int *nGroup);
 void stage_centers(skidgpu_ctx &c);
 void stage_set_groups(skidgpu_ctx &c, const int *piGroup, int nGroup, const skidgpu_pgroup *centres);

@@ -96,6 +96,58 @@ __global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
 	if (i < cnt) out[i] = (uint32_t)(lo + i);
 }
 
+// Multi-GPU ownership of movers: block-cyclic over the Morton-ordered mover list (block j of OWN_BLOCK
+// movers belongs to rank j % nranks).  Contiguous ranges put whole halos on one rank, and the ranks that
+// converged early then wait at every step's agreement point for the one that holds the largest halo
+// (measured on 2 GPUs: move 447 ms against 290 ms ideal); interleaved blocks give every rank a
+// statistically identical sample.
+constexpr int OWN_BLOCK = 256;
+__global__ void __launch_bounds__(256) k_owned_ids(int rank, int nranks, int own, uint32_t *out)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= own) return;
+	const int lb = i / OWN_BLOCK, off = i % OWN_BLOCK;
+	out[i] = (uint32_t)((lb * nranks + rank) * OWN_BLOCK + off);
+}
+__global__ void __launch_bounds__(256) k_mask_unowned(int m, int rank, int nranks, float *x, float *y, float *z)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m || (i / OWN_BLOCK) % nranks == rank) return;
+	x[i] = 0.0f;
+	y[i] = 0.0f;
+	z[i] = 0.0f;
+}
+static int owned_count(int m, int rank, int nranks)
+{
+	const int nb = (int)ceil_div(m, OWN_BLOCK);
+	int own = 0;
+	for (int j = rank; j < nb; j += nranks) own += (j == nb - 1) ? m - j * OWN_BLOCK : OWN_BLOCK;
+	return own;
+}
+// all owned movers active, in mover order
+static void init_active_list(skidgpu_ctx &c)
+{
+	if (c.nActive <= 0) return;
+	if (c.cyclic)
+		SK_LAUNCH(k_owned_ids, (unsigned)ceil_div(c.nActive, 256), 256, 0, c.stream, c.rank, c.nranks, c.nActive,
+		          c.actList.p);
+	else SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, c.stream, c.shardLo, c.nActive, c.actList.p);
+}
+void move_mask_unowned(skidgpu_ctx &c)
+{
+	if (c.nranks <= 1 || c.nMove <= 0) return;
+	if (!c.cyclic) {
+		const int m = c.nMove, lo = c.shardLo, hi = c.shardHi;
+		for (float *p : {c.mx.p, c.my.p, c.mz.p}) {
+			if (lo > 0) CK(cudaMemsetAsync(p, 0, sizeof(float) * lo, c.stream));
+			if (hi < m) CK(cudaMemsetAsync(p + hi, 0, sizeof(float) * (m - hi), c.stream));
+		}
+		return;
+	}
+	SK_LAUNCH(k_mask_unowned, (unsigned)ceil_div(c.nMove, 256), 256, 0, c.stream, c.nMove, c.rank, c.nranks, c.mx.p,
+	          c.my.p, c.mz.p);
+}
+
 struct StepArgs {
 	TreeView tv;
 	const float4 *entPos; // (x,y,z,fBall2)
@@ -934,15 +986,23 @@ __global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *to
 	}
 }
 
-// nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517)
-__global__ void __launch_bounds__(256) k_count_scatter(int nEnt, const float4 *entNR, const uint32_t *dT,
+// nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517).  Grid-stride over
+// [lo, hi) with one atomic per block (one per warp serialised 570 k same-address atomics per call).
+__global__ void __launch_bounds__(256) k_count_scatter(int lo, int hi, const float4 *entNR, const uint32_t *dT,
                                                        uint32_t *out)
 {
-	float T = __uint_as_float(dT[0]);
-	int e = blockIdx.x * blockDim.x + threadIdx.x;
-	bool alive = e < nEnt && entNR[e].z >= T;
-	uint32_t b = __ballot_sync(SK_FULL, alive);
-	if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (uint32_t)__popc(b));
+	__shared__ uint32_t s_cnt;
+	if (threadIdx.x == 0) s_cnt = 0;
+	__syncthreads();
+	const float T = __uint_as_float(dT[0]);
+	uint32_t mine = 0;
+	for (int e = lo + blockIdx.x * blockDim.x + threadIdx.x; e < hi; e += gridDim.x * blockDim.x)
+		mine += entNR[e].z >= T ? 1u : 0u;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(SK_FULL, mine, o);
+	if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+	__syncthreads();
+	if (threadIdx.x == 0 && s_cnt) atomicAdd(out, s_cnt);
 }
 
 __global__ void __launch_bounds__(256)
@@ -1066,8 +1126,13 @@ static int count_scatterers(skidgpu_ctx &c)
 	cudaStream_t s = c.stream;
 	uint32_t *cnt = c.dCount.alloc(4);
 	CK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t), s));
-	if (c.nEnt > 0)
-		SK_LAUNCH(k_count_scatter, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entNR.p, c.dT.p, cnt);
+	// every rank counts its slice of the (replicated) scatterers
+	const int lo = (int)((long long)c.nEnt * c.rank / c.nranks), hi = (int)((long long)c.nEnt * (c.rank + 1) / c.nranks);
+	if (hi > lo) {
+		unsigned g = (unsigned)ceil_div(hi - lo, 256 * 8);
+		SK_LAUNCH(k_count_scatter, g > 148u * 8u ? 148u * 8u : g, 256, 0, s, lo, hi, c.entNR.p, c.dT.p, cnt);
+	}
+	sk_reduce(c, cnt, 1, SK_I32, SK_SUM);
 	uint32_t h = 0;
 	CK(cudaMemcpyAsync(&h, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
@@ -1222,6 +1287,11 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.shardLo = (int)((long long)m * c.rank / c.nranks);
 	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
 	c.nActive = c.shardHi - c.shardLo;
+	// block-cyclic ownership on several GPUs (the per-mover lists of SKIDGPU_MOVE_KERNEL=list are indexed
+	// by id - shardLo and keep the contiguous range)
+	c.cyclic = c.nranks > 1 && move_kernel() != MOVE_LIST;
+	if (c.cyclic) c.nActive = owned_count(m, c.rank, c.nranks);
+	c.nOwned = c.nActive;
 	if (m > 0) {
 		uint32_t *fileIdx = c.actList2.alloc(m);
 		SK_LAUNCH(k_compact_idx2, (unsigned)ceil_div(n, 256), 256, 0, s, n, flags, scan, fileIdx);
@@ -1241,7 +1311,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.ldelta.alloc(m);
 		c.lhmin.alloc(m);
 		c.lcnt.alloc(m);
-		const int own = c.shardHi - c.shardLo;
+		const int own = c.nOwned;
 		if (move_kernel() == MOVE_LIST) c.mList.alloc((size_t)(own > 0 ? own : 1) * LIST_CAP);
 		c.mQueue.alloc(own > 0 ? own : 1);
 		if (move_kernel() == MOVE_TILE) {
@@ -1263,8 +1333,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p, c.ball2.p, c.lhmin.p, c.lcnt.p, c.listInitFactor);
 		c.actList.alloc(m);
 		c.actList2.alloc(m); // fileIdx no longer needed after k_init_movers (same stream)
-		if (c.nActive > 0)
-			SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.shardLo, c.nActive, c.actList.p);
+		init_active_list(c);
 	}
 	if (nMoveOut) *nMoveOut = m;
 
@@ -1326,8 +1395,12 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	while (nGlobal) {
 		int nl = 0;
 		kt.start();
+		const double ms0 = c.kernel_ms[0];
+		const int na0 = c.nActive;
 		for (int i = 0; i < 5; ++i) nl += one_step(c, sa, bNoPrune);
 		kt.stop(nl);
+		if (getenv("SKIDGPU_STEP_TRACE") && c.rank == 0)
+			fprintf(stderr, "ittr %d nActive %d ms5 %.3f\n", nIttr, na0, c.kernel_ms[0] - ms0);
 		// kdPruneInactive
 		uint32_t na = 0;
 		if (c.nActive > 0) {
@@ -1358,9 +1431,8 @@ void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb,
 	cudaStream_t s = c.stream;
 	StageTimer tm(c, 3);
 	// kdReactivateMove (kd.c:796-799)
-	c.nActive = c.shardHi - c.shardLo;
-	if (c.nActive > 0)
-		SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.shardLo, c.nActive, c.actList.p);
+	c.nActive = c.nOwned;
+	init_active_list(c);
 	c.tileStepsLeft = 0;
 	c.tileWindow = nSteps > 0 ? nSteps : 1;
 	StepArgs sa;

@@ -4,7 +4,8 @@ points (include/skidgpu.h: skidgpu_reduce_cb); the all-gather of converged mover
 FoF / centres is driven from here.
 
 What is sharded: kNN queries (contiguous Morton ranges; fBall2 and f64 density partials are summed),
-movers (contiguous ranges of the Morton-ordered mover list) and groups for unbinding (g % nranks).
+movers (block-cyclic over the Morton-ordered mover list: contiguous ranges leave whole halos on one
+rank and the others wait for it at every step) and groups for unbinding (g % nranks).
 What is replicated: particles, trees, scatterers, FoF, catalogue bookkeeping.
 
 The same code runs on CPU with the gloo backend on host buffers (tests/test_parallel_cpu.py).
@@ -51,6 +52,8 @@ class Reducer:
         self.stream = torch.cuda.ExternalStream(stream, device=device) if (stream and device.type == "cuda") else None
         self.calls = 0
         self.bytes = 0
+        self.host_s = 0.0      # host time spent inside the callback (per-step agreement points are latency bound)
+        self._alias = {}       # (ptr, count, dtype) -> tensor: the library reuses a handful of buffers
         self.cb = REDUCE_CB(self._call)
 
     def reduce_tensor(self, t, op):
@@ -65,8 +68,15 @@ class Reducer:
         self.bytes += t.numel() * t.element_size()
 
     def _call(self, user, ptr, count, dtype, op):
+        import time
+        t0 = time.perf_counter()
         try:
-            t = tensor_from_pointer(ptr, count, dtype, self.device)
+            key = (ptr, count, dtype)
+            t = self._alias.get(key)
+            if t is None:
+                t = tensor_from_pointer(ptr, count, dtype, self.device)
+                if count <= 16:  # only the small per-step buffers are worth caching (large ones get reallocated)
+                    self._alias[key] = t
             if dtype == 1 and op != 2:
                 # NCCL has no uint8 min/max guarantee across versions: widen flags through int32
                 w = t.to(torch.int32)
@@ -74,6 +84,7 @@ class Reducer:
                 t.copy_(w.to(torch.uint8))
             else:
                 self.reduce_tensor(t, op)
+            self.host_s += time.perf_counter() - t0
             return 0
         except Exception as e:  # never let an exception cross the C boundary
             print("skid_b200.parallel.Reducer:", e, flush=True)
@@ -121,7 +132,9 @@ def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks
         if nranks == 1 or sk.nMove == 0:
             return
         px, py, pz, nm, lo, hi = sk.mover_arrays()
-        reducer.allgather_owned([tensor_from_pointer(p, nm, 2, dev) for p in (px, py, pz)], lo, hi)
+        sk.mask_unowned_movers()  # ownership is block-cyclic: the library zeroes what other ranks own
+        for p in (px, py, pz):
+            reducer.reduce_tensor(tensor_from_pointer(p, nm, 2, dev), 2)
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
 
