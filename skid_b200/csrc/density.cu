@@ -161,17 +161,62 @@ __device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, ui
 	int lev = a.tv.top - 1;
 	uint32_t node = 0;
 	uint32_t mymask = 0;
+	// Leaf buckets (children of a level-0 node) are visited nearest box first: the bound tightens on the
+	// buckets that hold the true neighbours, and once the nearest unvisited box is outside the bound the
+	// whole node is done.  key0 = (box distance bits, child) of this lane's child, ~0 when visited/outside.
+	uint32_t key0 = 0xffffffffu;
 #define KNN_TEST_CHILDREN()                                                                            \
 	{                                                                                              \
 		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
 		float d = knn_box_d2<PER>(q, bx[0], bx[1]);                                            \
-		s_dist[lev][lane] = d;                                                                 \
-		uint32_t m_ = __ballot_sync(SK_FULL, d <= bound);                                      \
-		if (lane == lev) mymask = m_;                                                          \
-		__syncwarp();                                                                          \
+		if (lev == 0) key0 = d <= bound ? ((__float_as_uint(d) & ~31u) | (uint32_t)lane) : 0xffffffffu; \
+		else {                                                                                 \
+			s_dist[lev][lane] = d;                                                         \
+			uint32_t m_ = __ballot_sync(SK_FULL, d <= bound);                              \
+			if (lane == lev) mymask = m_;                                                  \
+			__syncwarp();                                                                  \
+		}                                                                                      \
 	}
 	KNN_TEST_CHILDREN();
 	while (true) {
+		if (lev == 0) {
+			const uint32_t kmin = __reduce_min_sync(SK_FULL, key0);
+			// (distance rounded down to a multiple of 32 ulp: never prunes a box that is inside the bound)
+			if (kmin == 0xffffffffu || __uint_as_float(kmin & ~31u) > bound) {
+				++lev;
+				if (lev >= a.tv.top) break;
+				node >>= 5;
+				continue;
+			}
+			const int c = (int)(kmin & 31u);
+			if (lane == c) key0 = 0xffffffffu;
+			const uint32_t child = node * 32 + c;
+			if ((int)child >= skipLo && (int)child <= skipHi) continue;
+			// leaf bucket: 32 points, one per lane
+			int idx = (int)child * 32 + lane;
+			bool valid = idx < n;
+			float4 p = a.pos4[valid ? idx : 0];
+			float d2 = knn_d2<PER>(q, p);
+			bool hit = valid && d2 <= bound;
+			uint32_t hm = __ballot_sync(SK_FULL, hit);
+			if (hm) {
+				if (hit) s_buf[cnt + __popc(hm & lt)] = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
+				cnt += __popc(hm);
+				__syncwarp();
+				if (cnt >= 32) {
+					uint64_t b = s_buf[lane];
+					kbest_merge(a0, a1, b, lane);
+					uint64_t t = (lane + 32 < cnt) ? s_buf[lane + 32] : KNN_INF;
+					__syncwarp();
+					s_buf[lane] = t;
+					__syncwarp();
+					cnt -= 32;
+					uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
+					bound = fminf(bound, __uint_as_float((uint32_t)(kth >> 32)));
+				}
+			}
+			continue;
+		}
 		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
 		if (m == 0) {
 			++lev;
@@ -183,37 +228,9 @@ __device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, ui
 		m &= m - 1;
 		if (lane == lev) mymask = m;
 		if (s_dist[lev][c] > bound) continue;
-		uint32_t child = node * 32 + c;
-		if (lev > 0) {
-			--lev;
-			node = child;
-			KNN_TEST_CHILDREN();
-			continue;
-		}
-		if ((int)child >= skipLo && (int)child <= skipHi) continue;
-		// leaf bucket: 32 points, one per lane
-		int idx = (int)child * 32 + lane;
-		bool valid = idx < n;
-		float4 p = a.pos4[valid ? idx : 0];
-		float d2 = knn_d2<PER>(q, p);
-		bool hit = valid && d2 <= bound;
-		uint32_t hm = __ballot_sync(SK_FULL, hit);
-		if (hm) {
-			if (hit) s_buf[cnt + __popc(hm & lt)] = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
-			cnt += __popc(hm);
-			__syncwarp();
-			if (cnt >= 32) {
-				uint64_t b = s_buf[lane];
-				kbest_merge(a0, a1, b, lane);
-				uint64_t t = (lane + 32 < cnt) ? s_buf[lane + 32] : KNN_INF;
-				__syncwarp();
-				s_buf[lane] = t;
-				__syncwarp();
-				cnt -= 32;
-				uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
-				bound = fminf(bound, __uint_as_float((uint32_t)(kth >> 32)));
-			}
-		}
+		--lev;
+		node = node * 32 + c;
+		KNN_TEST_CHILDREN();
 	}
 #undef KNN_TEST_CHILDREN
 }
