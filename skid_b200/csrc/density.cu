@@ -217,17 +217,19 @@ __device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, ui
 			}
 			continue;
 		}
-		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
-		if (m == 0) {
+		// upper levels: nearest child box first as well, so that the walk starts in the subtree that holds
+		// the query; when the nearest unvisited child is outside the bound the node is done
+		const uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
+		const uint32_t kq = ((m >> lane) & 1u) ? ((__float_as_uint(s_dist[lev][lane]) & ~31u) | (uint32_t)lane) : 0xffffffffu;
+		const uint32_t kmin = __reduce_min_sync(SK_FULL, kq);
+		if (kmin == 0xffffffffu || __uint_as_float(kmin & ~31u) > bound) {
 			++lev;
 			if (lev >= a.tv.top) break;
 			node >>= 5;
 			continue;
 		}
-		int c = __ffs(m) - 1;
-		m &= m - 1;
-		if (lane == lev) mymask = m;
-		if (s_dist[lev][c] > bound) continue;
+		const int c = (int)(kmin & 31u);
+		if (lane == lev) mymask = m & ~(1u << c);
 		--lev;
 		node = node * 32 + c;
 		KNN_TEST_CHILDREN();

@@ -17,7 +17,7 @@ for l in lines[start + 1:]:
         if sass_lines: break
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: cur = (m.group(1).split("/")[-1], int(m.group(2))); continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", l): sass_lines.append(cur)
+    if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", l): sass_lines.append(cur)
 print("ncu inst", len(inst), "sass inst", len(sass_lines))
 agg = collections.defaultdict(lambda: [0, 0])
 for (v, s, src), ln in zip(inst, sass_lines):
