@@ -339,7 +339,16 @@ def main():
                      "launches_per_step": st["move_launches"] / a.steps,
                      "avg_launch_ms": st["move_kernel_ms"] / max(st["move_launches"], 1),
                      "share_of_step": st["move_kernel_ms"] / ms_dev},
+        # second kernel family, for the north_star's "kNN walk vs HBM roofline" line (16k+24 B per query)
+        "roofline_knn": {"kernel": "k_knn_density", "bound": "hbm", "unit": "GB/s", "peak": peak,
+                         "bytes_per_query": 16 * fl["nSmooth"] + 24,
+                         "achieved": (n / (world if shard else 1)) * (16 * fl["nSmooth"] + 24) / (st["knn_ms"] / a.steps * 1e-3) / 1e9
+                         if st["knn_ms"] > 0 else None,
+                         "note": "on-chip bound by design: neighbouring queries share their neighbours through L1/L2 "
+                                 "(ncu: 33 B of DRAM traffic per query, issue-active 77 %)"},
     }
+    if out["roofline_knn"]["achieved"]:
+        out["roofline_knn"]["frac"] = out["roofline_knn"]["achieved"] / peak
     if shard:
         out["config"]["particles_total"] = n
         out["config"]["nccl_bytes_per_step"] = reducer.bytes // max(1, (W + a.steps + 1 + a.steps))
