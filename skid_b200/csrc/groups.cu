@@ -282,6 +282,23 @@ __device__ __forceinline__ float soft_dir(float d2, float twoh, int iSoftType)
 	return (float)a;
 }
 
+// Far field of SPLINE_POT (r >= twoh): dir = (float)(1.0/sqrt((double)d2)) in the reference.  ncu on the
+// massive-halo box (config 5): k_group_pot is issue bound and the double sqrt + double divide of every
+// pair were ~50 of its ~70 instructions.  MUFU.RSQ + two FMA-residual Newton steps give the correctly
+// rounded float in all but ~1e-3 of the cases (<= 1 ulp otherwise) without touching the FP64 pipe; pairs
+// inside the softening (r < twoh, where d2 < twoh^2 decides exactly like the reference's double
+// compare up to ties on the boundary, at which both branches agree) keep the double evaluation.
+__device__ __forceinline__ float far_dir(float d2)
+{
+	float y = rsqrtf(d2);
+	float g = d2 * y, h = 0.5f * y;
+	float r = fmaf(-g, h, 0.5f);
+	y = fmaf(y, r, y);
+	g = d2 * y, h = 0.5f * y;
+	r = fmaf(-g, h, 0.5f);
+	return fmaf(y, r, y);
+}
+
 // scoop sources (grav.c:63-135): ungrouped particles within fScoop of rCenter (periodic), found in
 // the tree over the ungrouped particles.  One warp per group.  MODE 0 counts, MODE 1 fills.
 struct ScoopArgs {
@@ -403,6 +420,7 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 	if (n >= a.nMaxMembers) return; // kd.c:1330
 	const int i = (blockIdx.x - a.tileStart[g]) * POT_T + tid;
 	const bool act = i < n;
+	const bool spline = a.iSoftType != SKIDGPU_PLUMMER;
 	float4 ri = make_float4(0, 0, 0, 0);
 	if (act) ri = a.qr[beg + i];
 	double pot = 0.0;
@@ -410,19 +428,24 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 		int j = j0 + tid;
 		if (j < n) {
 			s_r[tid] = a.qr[beg + j];
-			s_m[tid] = a.qv[beg + j].w;
+			s_m[tid] = __fmul_rn(a.G, a.qv[beg + j].w); // kd->G*p[j].fMass (grav.c:31-32), float
 		}
 		__syncthreads();
 		int lim = n - j0 < POT_T ? n - j0 : POT_T;
 		if (act) {
+#pragma unroll 4
 			for (int t = 0; t < lim; ++t) {
-				if (j0 + t == i) continue;
-				float4 rj = s_r[t];
-				float dx = __fsub_rn(ri.x, rj.x), dy = __fsub_rn(ri.y, rj.y), dz = __fsub_rn(ri.z, rj.z);
-				float d2 = dist2_rn(dx, dy, dz);
-				float twoh = __fadd_rn(ri.w, rj.w);
-				float dir = soft_dir(d2, twoh, a.iSoftType);
-				pot += (double)__fmul_rn(__fmul_rn(a.G, s_m[t]), dir); // grav.c:31-32
+				const float4 rj = s_r[t];
+				const float dx = __fsub_rn(ri.x, rj.x), dy = __fsub_rn(ri.y, rj.y), dz = __fsub_rn(ri.z, rj.z);
+				const float d2 = dist2_rn(dx, dy, dz);
+				const float twoh = __fadd_rn(ri.w, rj.w);
+				float dir;
+				if (spline && d2 >= twoh * twoh && d2 > 0.0f) dir = far_dir(d2);
+				else {
+					if (j0 + t == i) continue;
+					dir = soft_dir(d2, twoh, a.iSoftType);
+				}
+				pot += (double)__fmul_rn(s_m[t], dir);
 			}
 		}
 		__syncthreads();
@@ -440,18 +463,19 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 			ny = wrap_del(ny, a.L[1]);
 			nz = wrap_del(nz, a.L[2]);
 			s_r[tid] = make_float4(nx, ny, nz, a.softS[sidx]);
-			s_m[tid] = p.w;
+			s_m[tid] = __fmul_rn(a.G, p.w);
 		}
 		__syncthreads();
 		int lim = (int)(sn - j0 < (uint32_t)POT_T ? sn - j0 : (uint32_t)POT_T);
 		if (act) {
+#pragma unroll 4
 			for (int t = 0; t < lim; ++t) {
-				float4 rj = s_r[t];
-				float dx = __fsub_rn(rj.x, ri.x), dy = __fsub_rn(rj.y, ri.y), dz = __fsub_rn(rj.z, ri.z);
-				float d2 = dist2_rn(dx, dy, dz);
-				float twoh = __fadd_rn(rj.w, ri.w);
-				float dir = soft_dir(d2, twoh, a.iSoftType);
-				pot += (double)__fmul_rn(__fmul_rn(a.G, s_m[t]), dir);
+				const float4 rj = s_r[t];
+				const float dx = __fsub_rn(rj.x, ri.x), dy = __fsub_rn(rj.y, ri.y), dz = __fsub_rn(rj.z, ri.z);
+				const float d2 = dist2_rn(dx, dy, dz);
+				const float twoh = __fadd_rn(rj.w, ri.w);
+				const float dir = (spline && d2 >= twoh * twoh && d2 > 0.0f) ? far_dir(d2) : soft_dir(d2, twoh, a.iSoftType);
+				pot += (double)__fmul_rn(s_m[t], dir);
 			}
 		}
 		__syncthreads();
@@ -637,7 +661,8 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 				float dx = __fsub_rn(rs.x, r.x), dy = __fsub_rn(rs.y, r.y), dz = __fsub_rn(rs.z, r.z);
 				float d2 = dist2_rn(dx, dy, dz);
 				float twoh = __fadd_rn(rs.w, r.w);
-				float dir = soft_dir(d2, twoh, a.iSoftType);
+				float dir = (a.iSoftType != SKIDGPU_PLUMMER && d2 >= twoh * twoh && d2 > 0.0f) ? far_dir(d2)
+				                                                                             : soft_dir(d2, twoh, a.iSoftType);
 				pot[i] -= (double)__fmul_rn(__fmul_rn(a.G, ms), dir);
 			}
 		}
