@@ -290,7 +290,8 @@ __device__ __forceinline__ float soft_dir(float d2, float twoh, int iSoftType)
 // compare up to ties on the boundary, at which both branches agree) keep the double evaluation.
 __device__ __forceinline__ float far_dir(float d2)
 {
-	float y = rsqrtf(d2);
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(d2)); // d2 >= twoh^2: never denormal in practice (ftz -> inf -> near path values only if twoh = 0)
 	float g = d2 * y, h = 0.5f * y;
 	float r = fmaf(-g, h, 0.5f);
 	y = fmaf(y, r, y);
@@ -439,12 +440,9 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 				const float dx = __fsub_rn(ri.x, rj.x), dy = __fsub_rn(ri.y, rj.y), dz = __fsub_rn(ri.z, rj.z);
 				const float d2 = dist2_rn(dx, dy, dz);
 				const float twoh = __fadd_rn(ri.w, rj.w);
-				float dir;
-				if (spline && d2 >= twoh * twoh && d2 > 0.0f) dir = far_dir(d2);
-				else {
-					if (j0 + t == i) continue;
-					dir = soft_dir(d2, twoh, a.iSoftType);
-				}
+				float dir = far_dir(d2);
+				if (!(spline && d2 >= fmaxf(twoh * twoh, 1.0e-30f))) // inside the softening, Plummer, or the particle itself
+					dir = (j0 + t == i) ? 0.0f : soft_dir(d2, twoh, a.iSoftType);
 				pot += (double)__fmul_rn(s_m[t], dir);
 			}
 		}
@@ -474,7 +472,8 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 				const float dx = __fsub_rn(rj.x, ri.x), dy = __fsub_rn(rj.y, ri.y), dz = __fsub_rn(rj.z, ri.z);
 				const float d2 = dist2_rn(dx, dy, dz);
 				const float twoh = __fadd_rn(rj.w, ri.w);
-				const float dir = (spline && d2 >= twoh * twoh && d2 > 0.0f) ? far_dir(d2) : soft_dir(d2, twoh, a.iSoftType);
+				float dir = far_dir(d2);
+				if (!(spline && d2 >= fmaxf(twoh * twoh, 1.0e-30f))) dir = soft_dir(d2, twoh, a.iSoftType);
 				pot += (double)__fmul_rn(s_m[t], dir);
 			}
 		}
@@ -661,8 +660,8 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 				float dx = __fsub_rn(rs.x, r.x), dy = __fsub_rn(rs.y, r.y), dz = __fsub_rn(rs.z, r.z);
 				float d2 = dist2_rn(dx, dy, dz);
 				float twoh = __fadd_rn(rs.w, r.w);
-				float dir = (a.iSoftType != SKIDGPU_PLUMMER && d2 >= twoh * twoh && d2 > 0.0f) ? far_dir(d2)
-				                                                                             : soft_dir(d2, twoh, a.iSoftType);
+				float dir = far_dir(d2);
+				if (!(a.iSoftType != SKIDGPU_PLUMMER && d2 >= fmaxf(twoh * twoh, 1.0e-30f))) dir = soft_dir(d2, twoh, a.iSoftType);
 				pot[i] -= (double)__fmul_rn(__fmul_rn(a.G, ms), dir);
 			}
 		}
