@@ -459,10 +459,11 @@ __global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t 
 // Slow path of the tile build: the tiles in `queue` walk the tree themselves; nodes and leaf buckets are
 // pruned against the members (not only their bounding box), so a tile that straddles a Morton
 // discontinuity still gets a short list.
-// Short tiles: in the cores of dense clumps the ball radii are smaller than the 5-step reach and the
-// list explodes ((h + 5 fStep)^3 / h^3).  A tile whose list overflows with `reach` is rebuilt with
-// `reachShort` (one step) and appended to `shortQueue`: it is then walked again before EVERY step of
-// the window (one_step launches this kernel on the short queue with reach = 0).
+// Short tiles: in the cores of dense clumps the ball radii are smaller than the window's reach and the
+// list explodes ((h + 4 fStep)^3 / h^3).  A tile whose list overflows with `reach` is rebuilt with
+// `reachShort` (0: valid where the movers are now) and appended to `shortQueue`: it is then walked again
+// before EVERY step of the window (one_step launches this kernel on the short queue with reach < 0 =
+// "skip the first attempt").
 __global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a, const uint32_t *queue, const uint32_t *queueCount,
                                                    float reach, float reachShort, uint32_t *shortQueue,
                                                    uint32_t *shortCount)
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a, const uint3
 		float r = 0.0f;
 		for (int attempt = 0; attempt < 2 && overflow; ++attempt) {
 			const float rr = attempt == 0 ? reach : reachShort;
-			if (!(rr > 0.0f)) continue;
+			if (rr < 0.0f) continue; // attempt not wanted
 			r = rr * 1.001f + 4.0e-7f * amax; // slack for the rounding of the moves and of the tests
 			const float r2 = r * r;
 			float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f, z0 = 3.0e38f, z1 = -3.0e38f;
@@ -591,7 +592,8 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper
 		z0 = fminf(z0, __shfl_xor_sync(SK_FULL, z0, o));
 		z1 = fmaxf(z1, __shfl_xor_sync(SK_FULL, z1, o));
 	}
-	// reach = steps until the next rebuild x fStep; slack for the rounding of the moves and of the tests
+	// reach = moves until the last evaluation before the next rebuild x fStep; slack for the rounding of the
+	// moves and of the tests
 	const float r = reach * 1.001f + 4.0e-7f * fmaxf(fmaxf(fabsf(x0), fabsf(x1)),
 	                                                 fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(z0), fabsf(z1))));
 	const float r2 = r * r;
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 			cand = cand && s0 + lane < ns;
 			TILE_APPEND(cand, e);
 		}
-		if (overflow) { // too long for the 5-step reach: k_tile_walk retries and falls back to a one-step list
+		if (overflow) { // too long for the window's reach: k_tile_walk retries and falls back to a zero-reach list
 			if (lane == 0) a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
 			return;
 		}
@@ -1183,11 +1185,13 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	sa.nActive = c.nActive;
 	const int nSuper = (int)ceil_div(c.nTiles, SUPER);
 	CK(cudaMemsetAsync(c.dT.p + 5, 0, 2 * sizeof(uint32_t), s)); // short-tile queue, big slots in use
-	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, (float)steps * sa.fStep);
+	// a list built now is evaluated at the current positions and after 1 .. steps-1 moves of length fStep
+	const float reach = (float)(steps - 1) * sa.fStep;
+	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, reach);
 	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
 	// spread-out supertiles build per tile; tiles whose 5-step list overflows become short tiles (dT[5])
-	SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, s, sa, sa.tileQueue, sa.tileQueueCount, (float)steps * sa.fStep,
-	          steps > 1 ? sa.fStep : 0.0f, c.shortQueue.p, c.dT.p + 5);
+	SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, s, sa, sa.tileQueue, sa.tileQueueCount, reach,
+	          steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
 	c.tileFresh = true;
 	if (getenv("SKIDGPU_TILE_DIAG")) {
 		std::vector<int> h(c.nTiles);
@@ -1232,8 +1236,8 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 		if (mk == MOVE_TILE) {
 			if (c.tileStepsLeft <= 0) rebuild_tiles(c, sa, c.tileWindow);
 			--c.tileStepsLeft;
-			if (!c.tileFresh) // short tiles are rebuilt before every step (their list reaches one step)
-				SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, c.stream, sa, c.shortQueue.p, c.dT.p + 5, 0.0f, sa.fStep,
+			if (!c.tileFresh) // short tiles are rebuilt before every step (their list has no reach)
+				SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, c.stream, sa, c.shortQueue.p, c.dT.p + 5, -1.0f, 0.0f,
 				          (uint32_t *)nullptr, (uint32_t *)nullptr);
 			c.tileFresh = false;
 			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa);
