@@ -363,7 +363,10 @@ def main():
         except Exception as e:  # the reference binary did not travel
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"unavailable: {e}"}
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    torch.cuda.synchronize()
+    del dev
+    torch.cuda.empty_cache()  # nothing of torch's may outlive the context's stream
     sk.close()
     if dist is not None:
         dist.destroy_process_group()
