@@ -7,51 +7,110 @@
 #include <string.h>
 #include "skid_host.h"
 
+/* The three ASCII arrays are formatted in chunks on all host threads (fastio.c); the bytes are the
+ * ones fprintf("%d\n") / ("%.10g\n") / ("%g\n") would produce. */
+static char *fmt_group_chunk(void *arg, size_t lo, size_t hi, char *out)
+{
+	const int *piGroup = (const int *)arg;
+	size_t i;
+	for (i = lo; i < hi; ++i) {
+		out = fmt_int(out, piGroup[i]);
+		*out++ = '\n';
+	}
+	return out;
+}
+
 int out_group(const char *path, int n, const int *piGroup)
 {
 	FILE *fp = fopen(path, "w");
-	int i;
+	int rc;
 	if (!fp) return -1;
 	fprintf(fp, "%d\n", n);
-	for (i = 0; i < n; ++i) fprintf(fp, "%d\n", piGroup[i]);
-	return fclose(fp);
+	rc = chunked_write(fp, (size_t)(n > 0 ? n : 0), 12, fmt_group_chunk, (void *)piGroup);
+	return fclose(fp) | rc;
+}
+
+static char *fmt_density_chunk(void *arg, size_t lo, size_t hi, char *out)
+{
+	const float *rho = (const float *)arg;
+	size_t i;
+	for (i = lo; i < hi; ++i) {
+		out = fmt_g(out, rho[i], 10);
+		*out++ = '\n';
+	}
+	return out;
 }
 
 int out_density(const char *path, int n, const float *rho)
 {
 	FILE *fp = fopen(path, "w");
-	int i;
+	int rc;
 	if (!fp) return -1;
 	fprintf(fp, "%d\n", n);
-	for (i = 0; i < n; ++i) fprintf(fp, "%.10g\n", rho[i]);
-	return fclose(fp);
+	rc = chunked_write(fp, (size_t)(n > 0 ? n : 0), 40, fmt_density_chunk, (void *)rho);
+	return fclose(fp) | rc;
 }
 
 /* .ray: N, then every x displacement, every y, every z; movers get the min-image of
  * (final - initial), everything else a literal 0. */
+typedef struct {
+	const snapshot *s;
+	const int *slot; /* mover slot of particle i or -1 */
+	const float *r3;
+	float half;
+	int axis;
+} ray_state;
+
+static char *fmt_ray_chunk(void *arg, size_t lo, size_t hi, char *out)
+{
+	const ray_state *st = (const ray_state *)arg;
+	size_t i;
+	for (i = lo; i < hi; ++i) {
+		const int m = st->slot[i];
+		if (m >= 0) {
+			float d = st->r3[3 * (size_t)m + st->axis] - st->s->p[i].r[st->axis];
+			if (d > st->half) d -= 2 * st->half;
+			if (d <= -st->half) d += 2 * st->half;
+			out = fmt_g(out, d, 6);
+		} else {
+			*out++ = '0';
+		}
+		*out++ = '\n';
+	}
+	return out;
+}
+
 int out_vector(const char *path, const snapshot *s, int nMove, const int *iOrder, const float *r3,
                const float fPeriod[3])
 {
 	FILE *fp = fopen(path, "w");
-	int axis, i, m;
+	ray_state st;
+	int *slot;
+	int axis, i, m, rc = 0;
 	if (!fp) return -1;
 	fprintf(fp, "%d\n", s->n);
-	for (axis = 0; axis < 3; ++axis) {
-		const float half = 0.5 * fPeriod[axis];
-		m = 0;
-		for (i = 0; i < s->n; ++i) {
-			if (m < nMove && iOrder[m] == i) {
-				float d = r3[3 * m + axis] - s->p[i].r[axis];
-				if (d > half) d -= 2 * half;
-				if (d <= -half) d += 2 * half;
-				fprintf(fp, "%g\n", d);
-				++m;
-			} else {
-				fprintf(fp, "0\n");
-			}
-		}
+	/* the reference walks the movers in ascending iOrder next to the particles (kd.c:1577-1590):
+	 * a mover whose iOrder is out of sequence would be skipped there, so it is skipped here */
+	slot = (int *)malloc((size_t)(s->n ? s->n : 1) * sizeof(int));
+	if (!slot) {
+		fclose(fp);
+		return -1;
 	}
-	return fclose(fp);
+	m = 0;
+	for (i = 0; i < s->n; ++i) {
+		if (m < nMove && iOrder[m] == i) slot[i] = m++;
+		else slot[i] = -1;
+	}
+	st.s = s;
+	st.slot = slot;
+	st.r3 = r3;
+	for (axis = 0; axis < 3 && !rc; ++axis) {
+		st.half = 0.5 * fPeriod[axis];
+		st.axis = axis;
+		rc = chunked_write(fp, (size_t)s->n, 40, fmt_ray_chunk, &st);
+	}
+	free(slot);
+	return fclose(fp) | rc;
 }
 
 static void put_be32(FILE *fp, const void *v)
@@ -148,7 +207,7 @@ int out_stats(const char *path, const snapshot *s, const float *rho, const int *
 	fill = (int *)calloc((size_t)nGroup + 1, sizeof(int));
 	for (i = 0; i < s->n; ++i) start[piGroup[i] + 1]++;
 	for (ig = 0; ig < nGroup; ++ig) start[ig + 1] += start[ig];
-	all = (member *)malloc((size_t)(s->n ? s->n : 1) * sizeof(member));
+	all = (member *)malloc((size_t)(s->n > 0 ? s->n : 1) * sizeof(member));
 	for (i = 0; i < s->n; ++i) {
 		ig = piGroup[i];
 		all[start[ig] + fill[ig]++].idx = i;

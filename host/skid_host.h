@@ -34,6 +34,18 @@ int out_stats(const char *path, const snapshot *s, const float *rho, const int *
               const skidgpu_pgroup *g, const float fPeriod[3], float G, float z, double fExpHub,
               float fDensMin, float fTempMax);
 
+/* fastio.c: formatters byte-identical to printf's "%d" / "%.<prec>g", a pthread fork/join and an
+ * ordered chunked writer */
+#include <stddef.h>
+typedef void (*par_fn)(void *arg, size_t lo, size_t hi, int tid);
+typedef char *(*chunk_fmt_fn)(void *arg, size_t lo, size_t hi, char *out);
+int host_threads(void);
+void par_for(size_t n, size_t grain, par_fn fn, void *arg);
+char *fmt_int(char *out, int v);
+char *fmt_g(char *out, double v, int prec);
+int chunked_write(FILE *fp, size_t n, size_t max_per_item, chunk_fmt_fn fn, void *arg);
+size_t parse_ints(const char *text, size_t len, int *out, size_t n);
+
 /* csmExp2Hub (cosmo.c:46-58) */
 double cosmo_exp2hub(double dExp, double H0, double Omega0, double Lambda, double OmegaRad, double Quintess);
 
