@@ -20,13 +20,16 @@ skid_b200/csrc/%.o: skid_b200/csrc/%.cu $(CUHDR)
 skid_b200/libskidgpu.so: $(CUOBJ)
 	$(NVCC) -shared -o $@ $(CUOBJ) -gencode arch=compute_100a,code=sm_100a
 
-host: host/skid host/io_harness
+host: host/skid host/io_harness host/totipnat
 
 HOSTSRC = host/tipsy_io.c host/outputs.c host/cosmo.c host/fastio.c
 
 host/skid: host/skid_main.c $(HOSTSRC) host/skid_host.h include/skidgpu.h skid_b200/libskidgpu.so
 	$(CC) -O2 -Wall -Iinclude -pthread -o $@ host/skid_main.c $(HOSTSRC) \
 		-Lskid_b200 -lskidgpu -Wl,-rpath,'$$ORIGIN/../skid_b200' -lm
+
+host/totipnat: host/totipnat.c host/fastio.c host/skid_host.h include/skidgpu.h
+	$(CC) -O2 -Wall -Iinclude -pthread -o $@ host/totipnat.c host/fastio.c -lm
 
 # host-side I/O without the GPU library: test/benchmark harness for the readers and writers
 host/io_harness: tests/io_harness.c $(HOSTSRC) host/skid_host.h include/skidgpu.h
@@ -41,6 +44,6 @@ ref:
 	./oracle/build_ref.sh
 
 clean:
-	rm -f skid_b200/csrc/*.o skid_b200/libskidgpu.so host/skid host/io_harness oracle/liboracle.so
+	rm -f skid_b200/csrc/*.o skid_b200/libskidgpu.so host/skid host/io_harness host/totipnat oracle/liboracle.so
 
 .PHONY: all lib host oracle ref clean

@@ -169,102 +169,24 @@ int out_gtp(const char *path, int bStandard, double fTime, int nGroup, const ski
 	return fclose(fp);
 }
 
-/* ---- .stat ---------------------------------------------------------------------------- */
-typedef struct {
-	float rad2; /* squared distance from the group centre */
-	float rel[3];
-	int idx; /* file index */
-} member;
-
-static int cmp_member(const void *a, const void *b)
-{
-	float x = ((const member *)a)->rad2, y = ((const member *)b)->rad2;
-	return (x > y) - (x < y);
-}
-
-static int species(const snapshot *s, int i)
-{
-	if (i < s->nGas) return SKIDGPU_GAS;
-	if (i < s->nGas + s->nDark) return SKIDGPU_DARK;
-	return SKIDGPU_STAR;
-}
-
-int out_stats(const char *path, const snapshot *s, const float *rho, const int *piGroup, int nGroup,
-              const skidgpu_pgroup *g, const float fPeriod[3], float G, float z, double dExpHub,
-              float fDensMin, float fTempMax)
+/* ---- .stat ----------------------------------------------------------------------------
+ * kdOutStats' print statement (kd.c:1822-1836) over the accumulator rows computed on the device by
+ * skidgpu_stats (the per-group radial sort and sequential sums are GPU work, see csrc/stats.cu). */
+int out_stats(const char *path, int nGroup, const skidgpu_pgroup *g, const skidgpu_stat_row *row)
 {
 	FILE *fp = fopen(path, "w");
-	int *start, *fill;
-	member *all;
-	int i, k, ig;
-	const float fExp = 1.0 / (1.0 + z);
-	const float fExpHub = dExpHub;
-	float half[3];
+	int ig;
 	if (!fp) return -1;
-	for (k = 0; k < 3; ++k) half[k] = 0.5 * fPeriod[k];
-	/* bucket the members of every group (counting sort by group id) */
-	start = (int *)calloc((size_t)nGroup + 1, sizeof(int));
-	fill = (int *)calloc((size_t)nGroup + 1, sizeof(int));
-	for (i = 0; i < s->n; ++i) start[piGroup[i] + 1]++;
-	for (ig = 0; ig < nGroup; ++ig) start[ig + 1] += start[ig];
-	all = (member *)malloc((size_t)(s->n > 0 ? s->n : 1) * sizeof(member));
-	for (i = 0; i < s->n; ++i) {
-		ig = piGroup[i];
-		all[start[ig] + fill[ig]++].idx = i;
-	}
 	for (ig = 1; ig < nGroup; ++ig) {
-		member *q = all + start[ig];
-		const int n = start[ig + 1] - start[ig];
-		float fTotMass = 0.0, fGasMass = 0.0, fStarMass = 0.0, fHalfMass = 0.0;
-		float fVcirc = 0.0, fmVcirc = 0.0, flVcirc, fVdisp = 0.0, fRVmax = 0.0, fRhmass = 0.0;
-		int j;
+		const skidgpu_stat_row *r = &row[ig];
+		const int n = r->nMembers;
+		float fVdisp;
 		if (n <= 0) continue;
-		for (j = 0; j < n; ++j) {
-			const skidgpu_pinit *p = &s->p[q[j].idx];
-			float r2 = 0.0;
-			for (k = 0; k < 3; ++k) {
-				float d = p->r[k] - g[ig].rCenter[k];
-				if (d > half[k]) d -= 2 * half[k];
-				if (d <= -half[k]) d += 2 * half[k];
-				q[j].rel[k] = d;
-			}
-			for (k = 0; k < 3; ++k) r2 += q[j].rel[k] * q[j].rel[k];
-			q[j].rad2 = r2;
-		}
-		qsort(q, (size_t)n, sizeof(member), cmp_member);
-		for (j = 0; j < n; ++j) fHalfMass += 0.5 * s->p[q[j].idx].fMass;
-		for (j = 0; j < n; ++j) {
-			const skidgpu_pinit *p = &s->p[q[j].idx];
-			const int sp = species(s, q[j].idx);
-			fTotMass += p->fMass;
-			if (q[j].rad2 > 4.0 * p->fSoft * p->fSoft && G * fTotMass / sqrt(q[j].rad2) > fVcirc) {
-				fRVmax = sqrt(q[j].rad2);
-				fVcirc = G * fTotMass / fRVmax;
-			}
-			if (sp == SKIDGPU_GAS && rho[q[j].idx] >= fDensMin && p->fTemp <= fTempMax) fGasMass += p->fMass;
-			if (sp == SKIDGPU_STAR) fStarMass += p->fMass;
-			if (fTotMass > fHalfMass && fmVcirc == 0.0) {
-				fRhmass = sqrt(q[j].rad2);
-				fmVcirc = G * fTotMass / fRhmass;
-			}
-			for (k = 0; k < 3; ++k) {
-				float dv = fExp * (p->v[k] - g[ig].vcm[k]) + fExpHub * q[j].rel[k];
-				fVdisp += dv * dv;
-			}
-		}
-		flVcirc = G * fTotMass / sqrt(q[n - 1].rad2);
-		if (fVcirc == 0.0) {
-			fVcirc = flVcirc;
-			fRVmax = sqrt(q[n - 1].rad2);
-		}
-		fVdisp = sqrt(fVdisp / (3.0 * n));
-		fprintf(fp, "%d %d %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g\n", ig, n, fTotMass, fGasMass,
-		        fStarMass, sqrt(fVcirc), sqrt(fmVcirc), sqrt(flVcirc), fRVmax, fRhmass, sqrt(q[n - 1].rad2), fVdisp,
-		        g[ig].rCenter[0], g[ig].rCenter[1], g[ig].rCenter[2], g[ig].vcm[0], g[ig].vcm[1], g[ig].vcm[2],
-		        g[ig].rBound[0], g[ig].rBound[1], g[ig].rBound[2]);
+		fVdisp = sqrt(r->fVdispSum / (3.0 * n));
+		fprintf(fp, "%d %d %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g %g\n", ig, n, r->fTotMass, r->fGasMass,
+		        r->fStarMass, sqrt(r->fVcirc), sqrt(r->fmVcirc), sqrt(r->flVcirc), r->fRVmax, r->fRhmass,
+		        sqrt(r->fRouter2), fVdisp, g[ig].rCenter[0], g[ig].rCenter[1], g[ig].rCenter[2], g[ig].vcm[0],
+		        g[ig].vcm[1], g[ig].vcm[2], g[ig].rBound[0], g[ig].rBound[1], g[ig].rBound[2]);
 	}
-	free(all);
-	free(start);
-	free(fill);
 	return fclose(fp);
 }

@@ -29,10 +29,8 @@ int out_density(const char *path, int n, const float *rho);
 int out_vector(const char *path, const snapshot *s, int nMove, const int *iOrder, const float *r3,
                const float fPeriod[3]);
 int out_gtp(const char *path, int bStandard, double fTime, int nGroup, const skidgpu_pgroup *g);
-/* kdOutStats (kd.c:1703-1839) */
-int out_stats(const char *path, const snapshot *s, const float *rho, const int *piGroup, int nGroup,
-              const skidgpu_pgroup *g, const float fPeriod[3], float G, float z, double fExpHub,
-              float fDensMin, float fTempMax);
+/* print statement of kdOutStats (kd.c:1822-1836) over the rows of skidgpu_stats */
+int out_stats(const char *path, int nGroup, const skidgpu_pgroup *g, const skidgpu_stat_row *row);
 
 /* fastio.c: formatters byte-identical to printf's "%d" / "%.<prec>g", a pthread fork/join and an
  * ordered chunked writer */

@@ -263,8 +263,12 @@ int main(int argc, char **argv)
 		snprintf(achFile, sizeof achFile, "%s.gtp", o.achName);
 		out_gtp(achFile, o.bStandard, s.time, nGroup, cat);
 		if (o.bOutStats) {
+			/* kdOutStats, main.c:482-484 */
+			skidgpu_stat_row *rows = (skidgpu_stat_row *)calloc((size_t)nGroup + 1, sizeof(skidgpu_stat_row));
+			if (skidgpu_stats(ctx, o.G, o.z, fCosmo, o.fDensMin, o.fTempMax, rows)) die(ctx, "skidgpu_stats");
 			snprintf(achFile, sizeof achFile, "%s.stat", o.achName);
-			out_stats(achFile, &s, rho, piGroup, nGroup, cat, o.fPeriod, o.G, o.z, fCosmo, o.fDensMin, o.fTempMax);
+			out_stats(achFile, nGroup, cat, rows);
+			free(rows);
 		}
 	}
 	printf("SKID GPU Time:\n");

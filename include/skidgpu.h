@@ -173,6 +173,25 @@ int skidgpu_unbind(skidgpu_ctx *ctx, float fG, float z, double fCosmo, int iSoft
                    int *piGroup_by_iOrder, skidgpu_pgroup *g, int *nGroup, int *nUnbound,
                    int *nGroupBefore);
 
+/* kdOutStats (kd.c:1703-1839; main.c:482-484 "-stats"): per final group, the members sorted by distance
+ * from rCenter and the reference's sequential float32 accumulation, on the device.  Call after
+ * skidgpu_unbind.  rows: nGroup entries (entry 0 = non-group, zeroed).  fExpHub = a*H(a) as passed to
+ * skidgpu_unbind (kd.c:1731); fDensMin/fTempMax = the -d / -t cuts that define "gas mass" (kd.c:1792-1794).
+ * The writer prints, per group ig >= 1 (kd.c:1822-1836, every value with "%g"):
+ *   ig nMembers fTotMass fGasMass fStarMass sqrt(fVcirc) sqrt(fmVcirc) sqrt(flVcirc) fRVmax fRhmass
+ *   sqrt(fRouter2) (float)sqrt(fVdispSum/(3.0*nMembers)) rCenter[3] vcm[3] rBound[3]
+ * with the square roots taken in double on the float stored here. */
+typedef struct {
+	int nMembers;
+	float fTotMass, fGasMass, fStarMass;
+	float fVcirc, fmVcirc, flVcirc; /* G*M(<r)/r at the maximum, at the half-mass radius, at the outermost member */
+	float fRVmax, fRhmass;          /* radius of the maximum, half-mass radius */
+	float fRouter2;                 /* squared radius of the outermost member */
+	float fVdispSum;                /* sum over members and axes of dv^2 */
+} skidgpu_stat_row;
+int skidgpu_stats(skidgpu_ctx *ctx, float fG, float z, double fExpHub, float fDensMin, float fTempMax,
+                  skidgpu_stat_row *rows);
+
 /* Per-stage device time of the last call of each stage, in milliseconds (CUDA events on the
  * context's stream).  stage: 0 tree+density, 1 move, 2 fof, 3 microstep, 4 centres, 5 unbind. */
 double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage);

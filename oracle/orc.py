@@ -32,6 +32,8 @@ def lib():
         L.orc_fof.restype = i
         L.orc_unbind_group.argtypes = [i, vp, vp, vp, vp, i, vp, vp, vp, f, f, f, i, i, i, vp, vp, vp]
         L.orc_unbind_group.restype = i
+        L.orc_stats.argtypes = [i, vp, vp, vp, vp, vp, vp, i, i, vp, i, vp, vp, vp, f, f, C.c_double, f, f, vp]
+        L.orc_stats.restype = None
         _lib = L
     return _lib
 
@@ -109,3 +111,40 @@ def unbind_group(r, v, mass, soft, sr, smass, ssoft, G, z, fCosmo, iSoftType=2, 
     k = lib().orc_unbind_group(n, _p(r), _p(v), _p(mass), _p(soft), len(sr), _p(sr), _p(smass), _p(ssoft), G, z,
                                fCosmo, iSoftType, int(bNoUnbind), int(bSubPot), _p(removed), C.byref(bm), _p(vcm))
     return k, removed, bm.value, vcm
+
+
+STAT_ROW_DTYPE = np.dtype([("nMembers", "<i4"), ("fTotMass", "<f4"), ("fGasMass", "<f4"), ("fStarMass", "<f4"),
+                           ("fVcirc", "<f4"), ("fmVcirc", "<f4"), ("flVcirc", "<f4"), ("fRVmax", "<f4"),
+                           ("fRhmass", "<f4"), ("fRouter2", "<f4"), ("fVdispSum", "<f4")])
+
+
+def stats(pos, vel, mass, soft, temp, rho, nGas, nDark, grp, nGroup, rCenter, vcm, period, G, z, dExpHub,
+          fDensMin, fTempMax):
+    """kdOutStats accumulators per group (row 0 unused); rCenter/vcm: (nGroup, 3)."""
+    pos, vel, mass, soft, temp, rho = map(_f32, (pos, vel, mass, soft, temp, rho))
+    rc, vc = _f32(rCenter), _f32(vcm)
+    grp = np.ascontiguousarray(grp, np.int32)
+    per = _f32(period)
+    rows = np.zeros(nGroup, STAT_ROW_DTYPE)
+    lib().orc_stats(len(pos), _p(pos), _p(vel), _p(mass), _p(soft), _p(temp), _p(rho), nGas, nDark, _p(grp), nGroup,
+                    _p(rc), _p(vc), _p(per), G, z, dExpHub, fDensMin, fTempMax, _p(rows))
+    return rows
+
+
+def stat_lines(rows, rCenter, vcm, rBound):
+    """The text of a .stat file (kd.c:1811-1833) from accumulator rows; C's %g == Python's %g."""
+    out = []
+    for ig in range(1, len(rows)):
+        r = rows[ig]
+        n = int(r["nMembers"])
+        if n <= 0:
+            continue
+        f32 = np.float32
+        vals = [float(r["fTotMass"]), float(r["fGasMass"]), float(r["fStarMass"]),
+                float(np.sqrt(np.float64(r["fVcirc"]))), float(np.sqrt(np.float64(r["fmVcirc"]))),
+                float(np.sqrt(np.float64(r["flVcirc"]))), float(r["fRVmax"]), float(r["fRhmass"]),
+                float(np.sqrt(np.float64(r["fRouter2"]))),
+                float(f32(np.sqrt(np.float64(r["fVdispSum"]) / (3.0 * n))))]
+        vals += [float(v) for v in rCenter[ig]] + [float(v) for v in vcm[ig]] + [float(v) for v in rBound[ig]]
+        out.append("%d %d " % (ig, n) + " ".join("%g" % v for v in vals))
+    return out

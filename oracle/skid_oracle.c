@@ -594,3 +594,100 @@ int orc_unbind_group(int n, const float *r, const float *v, const float *mass, c
 	free(idx);
 	return nRemoved;
 }
+
+/* ---- kdOutStats (kd.c:1703-1839) ----------------------------------------------------------------
+ * Per group: members sorted by squared distance from rCenter (CmpRadius kd.c:1690-1700), then the
+ * reference's sequential float32 accumulation, expression by expression (the literals 0.5, 4.0, 3.0
+ * are doubles there, so those sub-expressions are evaluated in double). */
+typedef struct {
+	float rad2;
+	float rel[3];
+	int idx;
+} stat_member;
+
+static int cmp_stat_member(const void *a, const void *b)
+{
+	float x = ((const stat_member *)a)->rad2, y = ((const stat_member *)b)->rad2;
+	return (x > y) - (x < y);
+}
+
+void orc_stats(int n, const float *pos, const float *vel, const float *mass, const float *soft, const float *temp,
+               const float *rho, int nGas, int nDark, const int *piGroup, int nGroup, const float *rCenter,
+               const float *vcm, const float *period, float G, float z, double dExpHub, float fDensMin,
+               float fTempMax, orc_stat_row *rows)
+{
+	int *start = (int *)calloc((size_t)nGroup + 1, sizeof(int));
+	int *fill = (int *)calloc((size_t)nGroup + 1, sizeof(int));
+	stat_member *all = (stat_member *)malloc((size_t)(n > 0 ? n : 1) * sizeof(stat_member));
+	const float fExp = 1.0 / (1.0 + z);
+	const float fExpHub = dExpHub;
+	float half[3];
+	int i, k, ig;
+	for (k = 0; k < 3; ++k) half[k] = 0.5 * period[k];
+	memset(rows, 0, (size_t)nGroup * sizeof(orc_stat_row));
+	for (i = 0; i < n; ++i) start[piGroup[i] + 1]++;
+	for (ig = 0; ig < nGroup; ++ig) start[ig + 1] += start[ig];
+	for (i = 0; i < n; ++i) {
+		ig = piGroup[i];
+		all[start[ig] + fill[ig]++].idx = i;
+	}
+	for (ig = 1; ig < nGroup; ++ig) {
+		stat_member *q = all + start[ig];
+		const int nm = start[ig + 1] - start[ig];
+		float fTotMass = 0.0, fGasMass = 0.0, fStarMass = 0.0, fHalfMass = 0.0;
+		float fVcirc = 0.0, fmVcirc = 0.0, flVcirc, fVdisp = 0.0, fRVmax = 0.0, fRhmass = 0.0;
+		int j;
+		if (nm <= 0) continue;
+		for (j = 0; j < nm; ++j) {
+			const int p = q[j].idx;
+			float r2 = 0.0;
+			for (k = 0; k < 3; ++k) {
+				float d = pos[3 * p + k] - rCenter[3 * ig + k];
+				if (d > half[k]) d -= 2 * half[k];
+				if (d <= -half[k]) d += 2 * half[k];
+				q[j].rel[k] = d;
+			}
+			for (k = 0; k < 3; ++k) r2 += q[j].rel[k] * q[j].rel[k];
+			q[j].rad2 = r2;
+		}
+		qsort(q, (size_t)nm, sizeof(stat_member), cmp_stat_member);
+		for (j = 0; j < nm; ++j) fHalfMass += 0.5 * mass[q[j].idx];
+		for (j = 0; j < nm; ++j) {
+			const int p = q[j].idx;
+			fTotMass += mass[p];
+			if (q[j].rad2 > 4.0 * soft[p] * soft[p] && G * fTotMass / sqrt(q[j].rad2) > fVcirc) {
+				fRVmax = sqrt(q[j].rad2);
+				fVcirc = G * fTotMass / fRVmax;
+			}
+			if (p < nGas && rho[p] >= fDensMin && temp[p] <= fTempMax) fGasMass += mass[p];
+			if (p >= nGas + nDark) fStarMass += mass[p];
+			if (fTotMass > fHalfMass && fmVcirc == 0.0) {
+				fRhmass = sqrt(q[j].rad2);
+				fmVcirc = G * fTotMass / fRhmass;
+			}
+			for (k = 0; k < 3; ++k) {
+				float dv = fExp * (vel[3 * p + k] - vcm[3 * ig + k]) + fExpHub * q[j].rel[k];
+				fVdisp += dv * dv;
+			}
+		}
+		flVcirc = G * fTotMass / sqrt(q[nm - 1].rad2);
+		if (fVcirc == 0.0) {
+			fVcirc = flVcirc;
+			fRVmax = sqrt(q[nm - 1].rad2);
+		}
+		rows[ig].nMembers = nm;
+		rows[ig].fTotMass = fTotMass;
+		rows[ig].fGasMass = fGasMass;
+		rows[ig].fStarMass = fStarMass;
+		rows[ig].fVcirc = fVcirc;
+		rows[ig].fmVcirc = fmVcirc;
+		rows[ig].flVcirc = flVcirc;
+		rows[ig].fRVmax = fRVmax;
+		rows[ig].fRhmass = fRhmass;
+		rows[ig].fRouter2 = q[nm - 1].rad2;
+		rows[ig].fVdispSum = fVdisp;
+	}
+	free(all);
+	free(start);
+	free(fill);
+}

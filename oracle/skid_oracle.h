@@ -63,6 +63,22 @@ int orc_unbind_group(int n, const float *r, const float *v, const float *mass, c
                      int iSoftType, int bNoUnbind, int bSubPot, unsigned char *removed, double *boundMass,
                      double *vcm);
 
+/* kdOutStats (kd.c:1703-1839): the accumulators behind one .stat line.  The writer prints
+ * ig, nMembers, fTotMass, fGasMass, fStarMass, sqrt(fVcirc), sqrt(fmVcirc), sqrt(flVcirc), fRVmax, fRhmass,
+ * sqrt(fRouter2), (float)sqrt(fVdispSum/(3.0*nMembers)), rCenter, vcm, rBound with "%g".  pos/vel: n*3;
+ * rCenter/vcm: nGroup*3 (row 0 unused); species by index range (gas, dark, star). */
+typedef struct {
+	int nMembers;
+	float fTotMass, fGasMass, fStarMass;
+	float fVcirc, fmVcirc, flVcirc;
+	float fRVmax, fRhmass, fRouter2;
+	float fVdispSum;
+} orc_stat_row;
+void orc_stats(int n, const float *pos, const float *vel, const float *mass, const float *soft, const float *temp,
+               const float *rho, int nGas, int nDark, const int *piGroup, int nGroup, const float *rCenter,
+               const float *vcm, const float *period, float G, float z, double dExpHub, float fDensMin,
+               float fTempMax, orc_stat_row *rows);
+
 #ifdef __cplusplus
 }
 #endif

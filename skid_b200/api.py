@@ -21,6 +21,11 @@ INT_MAX = 2 ** 31 - 1
 DARK, GAS, STAR = 1, 2, 4
 PLUMMER, SPLINE = 1, 2
 
+# skidgpu_stat_row (include/skidgpu.h)
+STAT_ROW_DTYPE = np.dtype([("nMembers", "<i4"), ("fTotMass", "<f4"), ("fGasMass", "<f4"), ("fStarMass", "<f4"),
+                           ("fVcirc", "<f4"), ("fmVcirc", "<f4"), ("flVcirc", "<f4"), ("fRVmax", "<f4"),
+                           ("fRhmass", "<f4"), ("fRouter2", "<f4"), ("fVdispSum", "<f4")])
+
 LOG_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int)
 
 _lib = None
@@ -31,7 +36,7 @@ EXPORTS = [
     "skidgpu_set_particles_dev", "skidgpu_set_soft", "skidgpu_density", "skidgpu_keep_neighbors",
     "skidgpu_get_neighbors", "skidgpu_move", "skidgpu_keep_step0", "skidgpu_get_step0", "skidgpu_fof",
     "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_moved_dev", "skidgpu_centers", "skidgpu_set_groups",
-    "skidgpu_unbind", "skidgpu_stage_ms", "skidgpu_counter", "skidgpu_debug_sort", "skidgpu_debug_scan",
+    "skidgpu_unbind", "skidgpu_stats", "skidgpu_stage_ms", "skidgpu_counter", "skidgpu_debug_sort", "skidgpu_debug_scan",
     "skidgpu_kernel_ms", "skidgpu_stream", "skidgpu_set_reduce_cb", "skidgpu_mover_arrays", "skidgpu_mask_unowned_movers",
 ]
 
@@ -68,6 +73,7 @@ def load_library():
     lib.skidgpu_centers.argtypes = [vp, vp, vp]
     lib.skidgpu_set_groups.argtypes = [vp, vp, i, vp]
     lib.skidgpu_unbind.argtypes = [vp, f, f, d, i, f, i, i, i, vp, vp, P(i), P(i), P(i)]
+    lib.skidgpu_stats.argtypes = [vp, f, f, d, f, f, vp]
     lib.skidgpu_stage_ms.argtypes = [vp, i]
     lib.skidgpu_stage_ms.restype = d
     lib.skidgpu_counter.argtypes = [vp, i]
@@ -244,6 +250,12 @@ class SkidGPU:
         self.nGroup = ng.value
         return grp, cat[:ng.value], nu.value, nb.value
 
+    def kdOutStats(self, G=1.0, z=0.0, fExpHub=0.0, fDensMin=0.0, fTempMax=FLT_MAX):
+        """Accumulator rows behind the .stat file (kd.c:1703-1839), one per final group (row 0 unused)."""
+        rows = np.zeros(max(self.nGroup, 1), STAT_ROW_DTYPE)
+        self._ck(self.lib.skidgpu_stats(self.h, G, z, fExpHub, fDensMin, fTempMax, _ptr(rows)))
+        return rows
+
     def debug_sort(self, keys, vals, bits):
         keys = np.ascontiguousarray(keys, np.uint64).copy()
         vals = np.ascontiguousarray(vals, np.uint32).copy()
@@ -276,7 +288,7 @@ def run_skid(pinit, nGas, nDark, nStar, tau, nSmooth=64, fDensMin=0.0, fTempMax=
              fCvg=None, fScoop=None, nMembers=8, nMaxMembers=INT_MAX, bNoUnbind=False, bGasAndDark=False,
              bGasOnly=False, bForceInitialCut=False, bNoPrune=False, period=None, center=(0.0, 0.0, 0.0),
              z=0.0, Omega0=1.0, Lambda=0.0, Quintess=0.0, G=1.0, H0=0.0, iSoftType=SPLINE, fEps=None, device=0,
-             want_arrays=True, ctx=None):
+             want_arrays=True, ctx=None, want_stats=False):
     """The stage script of main.c:343-471 on one GPU.  Returns a dict of results."""
     tau = float(np.float32(tau))
     if fCvg is None:
@@ -308,6 +320,9 @@ def run_skid(pinit, nGas, nDark, nStar, tau, nSmooth=64, fDensMin=0.0, fTempMax=
         a32 = f32(1.0 / (1.0 + z))                  # kd.c:1317: fShift is a float
         fCosmo = a32 * csmExp2Hub(a32, f32(H0), f32(Omega0), f32(Lambda), 0.0, f32(Quintess))
         grp, cat, nUnbound, nBefore = sk.kdUnbind(G, z, fCosmo, iSoftType, fScoop, bNoUnbind, nMaxMembers, nMembers)
+        if want_stats:                               # main.c:482-484
+            out["stat_rows"] = sk.kdOutStats(G, z, fCosmo, fDensMin, fTempMax)
+            out["fCosmo"] = fCosmo
         out.update(grp=grp, cat=cat, nUnbound=nUnbound, nGroupBefore=nBefore, nGroup=sk.nGroup - 1,
                    log=list(sk.log), stage_ms=sk.stage_ms(), mover_steps=sk.counter(1), launches=sk.counter(0))
     finally:

@@ -354,6 +354,15 @@ extern "C" int skidgpu_unbind(skidgpu_ctx *ctx, float fG, float z, double fCosmo
 	API_END(ctx)
 }
 
+extern "C" int skidgpu_stats(skidgpu_ctx *ctx, float fG, float z, double fExpHub, float fDensMin, float fTempMax,
+                             skidgpu_stat_row *rows)
+{
+	API_BEGIN(ctx)
+	if (!rows) throw SkidError("skidgpu_stats: null output array");
+	stage_stats(*ctx, fG, z, fExpHub, fDensMin, fTempMax, rows);
+	API_END(ctx)
+}
+
 extern "C" double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage)
 {
 	if (!ctx || stage < 0 || stage > 5) return -1.0;

@@ -154,6 +154,9 @@ void stage_set_groups(skidgpu_ctx &c, const int *piGroup, int nGroup, const skid
 void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmo, int iSoftType, float fScoop,
                   int bNoUnbind, int nMaxMembers, int nMinMembers, int *nUnbound, int *nGroupBefore);
 
+void stage_stats(skidgpu_ctx &c, float fG, float z, double dExpHub, float fDensMin, float fTempMax,
+                 skidgpu_stat_row *hostRows);
+
 struct StageTimer {
 	skidgpu_ctx &c;
 	int stage;

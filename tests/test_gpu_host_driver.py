@@ -113,3 +113,17 @@ def test_live_reference_unbind_restart(tmp_path):
     assert abs(a["nGroup"] - b["nGroup"]) <= 1
     gr, gg = tipsy.read_array(str(tmp_path / "ref.grp")), tipsy.read_array(str(tmp_path / "gpu.grp"))
     assert np.mean(canonical_labels(gr.astype(np.int64)) == canonical_labels(gg.astype(np.int64))) >= 0.999
+
+
+def test_demo_pipeline_native(demo_files, tmp_path, demo_input):
+    """The reference's demo line verbatim (demo:2): `totipnat < dark.std | skid ... ` with native input gives
+    byte-identical .grp/.den/.ray to the -std run."""
+    pre, _ = demo_files
+    std = os.path.join(os.path.dirname(pre), "dark.std")
+    nat = subprocess.run([os.path.join(ROOT, "host", "totipnat")], stdin=open(std, "rb"), capture_output=True)
+    assert nat.returncode == 0
+    args = [a for a in DEMO_ARGS if a != "-std"] + ["-o", str(tmp_path / "nat")]
+    r = subprocess.run([EXE] + args, input=nat.stdout, capture_output=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    for ext in ("grp", "den", "ray", "stat"):
+        assert open(pre + "." + ext, "rb").read() == open(str(tmp_path / "nat") + "." + ext, "rb").read(), ext

@@ -63,3 +63,41 @@ def test_writers_reproduce_reference_md5(harness, tmp_path, demo_golden):
     for ext in ("grp", "den", "ray"):
         md5 = hashlib.md5(open(tmp_path / ("out." + ext), "rb").read()).hexdigest()
         assert md5 == str(demo_golden["md5_" + ext]), ext
+
+
+def _demo_std(tmp_path, demo_input):
+    from skid_b200 import tipsy
+    p, ng, nd, ns, t = demo_input
+    f = str(tmp_path / "dark.std")
+    gas, dark, star = tipsy.pinit_to_records(p, ng, nd, ns)
+    tipsy.write_tipsy(f, t, gas, dark, star, standard=True)
+    return f
+
+
+# md5 of `totipnat_ref < demo.std` (the unmodified reference converter built by oracle/build_ref.sh) where
+# demo.std is the demo snapshot as rewritten from tests/golden/demo_input.npz by _demo_std below
+TOTIPNAT_DEMO_MD5 = "80a3975d674db861a4990104449816c6"
+
+
+def test_totipnat_matches_reference_converter(harness, tmp_path, demo_input):
+    """host/totipnat (std -> native, the first stage of the reference's demo pipeline, demo:2): same bytes as
+    the reference's converter on the demo snapshot (recorded md5, and live when oracle/_ref is present);
+    a two-snapshot stream converts both; the native file reads back to the same particles."""
+    from oracle import refdump
+    from skid_b200 import tipsy
+    exe = os.path.join(ROOT, "host", "totipnat")
+    subprocess.run(["make", "-C", ROOT, "host/totipnat"], check=True, capture_output=True)
+    std = _demo_std(tmp_path, demo_input)
+    raw = open(std, "rb").read()
+    r = subprocess.run([exe], input=raw, capture_output=True)
+    assert r.returncode == 0 and r.stderr.decode().strip() == "read time 1.000000"
+    assert hashlib.md5(r.stdout).hexdigest() == TOTIPNAT_DEMO_MD5
+    r2 = subprocess.run([exe], input=raw + raw, capture_output=True)
+    assert r2.stdout == r.stdout + r.stdout
+    if refdump.have_ref():
+        ref = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "totipnat_ref")], input=raw, capture_output=True)
+        assert ref.stdout == r.stdout
+    nat = str(tmp_path / "dark.nat")
+    open(nat, "wb").write(r.stdout)
+    a, b = tipsy.read_tipsy(std, standard=True), tipsy.read_tipsy(nat, standard=False)
+    assert a["nDark"] == b["nDark"] == 32768 and a["pinit"].tobytes() == b["pinit"].tobytes()

@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import DEMO, ROOT
+from conftest import DEMO, GOLDEN, ROOT
 
 sys.path.insert(0, ROOT)
 
@@ -152,3 +152,28 @@ def test_oracle_unbind(orc, demo_input, demo_golden):
                 assert abs(bm - cat1["fMass"][g]) <= 1e-4 * cat1["fMass"][g]
     assert abs(total_removed - int(demo_golden["nUnbound"])) <= 20     # 4134
     assert exact_groups >= 100                                           # 105/120 identical
+
+
+def test_stats_match_reference_stat_file(orc, demo_input, demo_golden):
+    """orc_stats (kdOutStats kd.c:1703-1839) on the reference's own final groups, centres and velocities
+    reproduces the reference's dark.stat line by line (text-identical "%g" columns)."""
+    from skid_b200.api import csmExp2Hub
+    p, ng, nd, ns, _ = demo_input
+    ref_lines = open(os.path.join(GOLDEN, "demo.stat")).read().strip().splitlines()
+    ref = np.array([[float(t) for t in ln.split()] for ln in ref_lines])
+    nGroup = len(ref_lines) + 1
+    rc = np.zeros((nGroup, 3), np.float32)
+    vc = np.zeros((nGroup, 3), np.float32)
+    rb = np.zeros((nGroup, 3), np.float32)
+    rc[1:], vc[1:] = demo_golden["gtp_pos"], demo_golden["gtp_vel"]
+    rb[1:] = ref[:, 18:21]
+    f32 = lambda v: float(np.float32(v))
+    fExp = f32(1.0)
+    dExpHub = fExp * csmExp2Hub(fExp, f32(DEMO["H0"]), 1.0, 0.0)
+    rows = orc.stats(p["r"], p["v"], p["fMass"], p["fSoft"], p["fTemp"], demo_golden["density"], ng, nd,
+                     demo_golden["grp"], nGroup, rc, vc, (1.0, 1.0, 1.0), 1.0, 0.0, dExpHub, DEMO["fDensMin"],
+                     3.4028234663852886e38)
+    lines = orc.stat_lines(rows, rc, vc, rb)
+    assert len(lines) == len(ref_lines) == 68
+    same = sum(a.split()[:18] == b.split()[:18] for a, b in zip(lines, ref_lines))
+    assert same == 68, [(a, b) for a, b in zip(lines, ref_lines) if a.split()[:18] != b.split()[:18]][:3]
