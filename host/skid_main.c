@@ -7,9 +7,11 @@
  */
 #include <float.h>
 #include <limits.h>
+#include <pthread.h>
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include "skid_host.h"
 
 #define PRUNE_STEPS 5
@@ -178,6 +180,67 @@ static void print_time(const char *label, double ms)
 	printf("%s%ld.%06ld\n", label, us / 1000000, us % 1000000);
 }
 
+/* The ASCII writers run on a helper thread while the GPU works on the next stage (the .den is formatted
+ * during the move loop, the .ray during unbinding): their inputs are final by then. */
+typedef struct {
+	pthread_t th;
+	int running, rc;
+	int (*fn)(void *);
+	void *arg;
+} bg_job;
+
+static void *bg_tramp(void *p)
+{
+	bg_job *j = (bg_job *)p;
+	j->rc = j->fn(j->arg);
+	return NULL;
+}
+
+static void bg_start(bg_job *j, int (*fn)(void *), void *arg)
+{
+	j->fn = fn;
+	j->arg = arg;
+	j->rc = 0;
+	j->running = pthread_create(&j->th, NULL, bg_tramp, j) == 0;
+	if (!j->running) j->rc = fn(arg);
+}
+
+static int bg_wait(bg_job *j)
+{
+	if (j->running) {
+		pthread_join(j->th, NULL);
+		j->running = 0;
+	}
+	return j->rc;
+}
+
+typedef struct {
+	char path[300];
+	const snapshot *s;
+	const float *rho, *mvR, *fPeriod;
+	const int *mvOrder;
+	int nMove;
+} write_job;
+
+static int job_density(void *p)
+{
+	const write_job *w = (const write_job *)p;
+	return out_density(w->path, w->s->n, w->rho);
+}
+
+static int job_vector(void *p)
+{
+	const write_job *w = (const write_job *)p;
+	return out_vector(w->path, w->s, w->nMove, w->mvOrder, w->mvR, w->fPeriod);
+}
+
+static double wall(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
 int main(int argc, char **argv)
 {
 	options o;
@@ -189,6 +252,11 @@ int main(int argc, char **argv)
 	float fStep;
 	int nGroup = 1, nMove = 0, nIttr = 0, nUnbound = 0, nBefore = 0, nExtra = 0;
 	char achFile[300];
+	bg_job denJob = {0}, rayJob = {0};
+	write_job denArgs, rayArgs;
+	int *mvOrder = NULL;
+	float *mvR = NULL;
+	double t0 = wall(), tRead, tInit, tStages, tEnd; /* host wall clock, reported with SKID_HOST_TIMING=1 */
 
 	printf("SKID v1.4.1 (B200 GPU hot path): group finder compatible with SKID v1.4.1, Stadel 2000\n");
 	parse_args(argc, argv, &o);
@@ -200,11 +268,13 @@ int main(int argc, char **argv)
 	}
 	printf("nDark:%d nGas:%d nStar:%d\n", s.nDark, s.nGas, s.nStar);
 	fflush(stdout);
+	tRead = wall();
 
 	if (skidgpu_create(&ctx, o.iDevice, o.fPeriod, o.fCenter, o.bPeriodic, o.bOutDiag)) die(NULL, "skidgpu_create");
 	if (skidgpu_set_particles(ctx, s.p, s.n, s.nGas, s.nDark, s.nStar)) die(ctx, "skidgpu_set_particles");
 	piGroup = (int *)calloc((size_t)s.n, sizeof(int));
 	rho = (float *)calloc((size_t)s.n, sizeof(float));
+	tInit = wall();
 
 	if (o.bUnbindOnly) {
 		/* main.c:349-373: strip a trailing .grp, read <name>.grp and, if present, <name>.gtp */
@@ -220,13 +290,13 @@ int main(int argc, char **argv)
 		if (rc < 0) return 1;
 		if (skidgpu_set_groups(ctx, piGroup, nGroup, rc ? cat : NULL)) die(ctx, "skidgpu_set_groups");
 	} else {
-		int *mvOrder = NULL;
-		float *mvR = NULL;
 		if (skidgpu_density(ctx, o.nSmooth, o.bGasAndDark, o.bGasOnly, rho, NULL, &nExtra)) die(ctx, "skidgpu_density");
 		if (o.bPeriodic) printf("nExtraScat:%d\n", nExtra);
 		if (o.bOutDens) {
-			snprintf(achFile, sizeof achFile, "%s.den", o.achName);
-			out_density(achFile, s.n, rho);
+			snprintf(denArgs.path, sizeof denArgs.path, "%s.den", o.achName);
+			denArgs.s = &s;
+			denArgs.rho = rho;
+			bg_start(&denJob, job_density, &denArgs);
 		}
 		if (skidgpu_move(ctx, o.fDensMin, o.fTempMax, o.fMassMax, o.fCvg, fStep, o.bForceInitialCut, o.bNoPrune,
 		                 log_cb, NULL, &nMove, &nIttr))
@@ -237,10 +307,14 @@ int main(int argc, char **argv)
 			mvOrder = (int *)malloc((size_t)(nMove ? nMove : 1) * sizeof(int));
 			mvR = (float *)malloc((size_t)(nMove ? nMove : 1) * 3 * sizeof(float));
 			if (skidgpu_get_moved(ctx, mvOrder, mvR)) die(ctx, "skidgpu_get_moved");
-			snprintf(achFile, sizeof achFile, "%s.ray", o.achName);
-			out_vector(achFile, &s, nMove, mvOrder, mvR, o.fPeriod);
-			free(mvOrder);
-			free(mvR);
+			bg_wait(&denJob); /* one set of writer threads at a time */
+			snprintf(rayArgs.path, sizeof rayArgs.path, "%s.ray", o.achName);
+			rayArgs.s = &s;
+			rayArgs.nMove = nMove;
+			rayArgs.mvOrder = mvOrder;
+			rayArgs.mvR = mvR;
+			rayArgs.fPeriod = o.fPeriod;
+			bg_start(&rayJob, job_vector, &rayArgs);
 		}
 		cat = (skidgpu_pgroup *)calloc((size_t)nGroup + 1, sizeof(skidgpu_pgroup));
 		if (skidgpu_centers(ctx, NULL, NULL)) die(ctx, "skidgpu_centers");
@@ -258,6 +332,8 @@ int main(int argc, char **argv)
 		printf("Number of particles Unbound:%d\n", nUnbound);
 		printf("Number of Groups:%d\n", nGroup - 1);
 		fflush(stdout);
+		tStages = wall();
+		if (bg_wait(&denJob) | bg_wait(&rayJob)) fprintf(stderr, "WARNING: could not write the .den/.ray file\n");
 		snprintf(achFile, sizeof achFile, "%s.grp", o.achName);
 		out_group(achFile, s.n, piGroup);
 		snprintf(achFile, sizeof achFile, "%s.gtp", o.achName);
@@ -280,7 +356,15 @@ int main(int argc, char **argv)
 	}
 	if (!o.bNoUnbind) print_time("   Unbinding:          ", skidgpu_stage_ms(ctx, 5));
 	fflush(stdout);
+	tEnd = wall();
+	if (getenv("SKID_HOST_TIMING"))
+		fprintf(stderr,
+		        "{\"host_wall_s\": {\"read\": %.3f, \"create_upload\": %.3f, \"stages_with_overlapped_writers\": %.3f, "
+		        "\"final_writers\": %.3f, \"total\": %.3f}, \"n\": %d, \"threads\": %d}\n",
+		        tRead - t0, tInit - tRead, tStages - tInit, tEnd - tStages, tEnd - t0, s.n, host_threads());
 	skidgpu_destroy(ctx);
+	free(mvOrder);
+	free(mvR);
 	free(piGroup);
 	free(rho);
 	free(cat);
