@@ -234,6 +234,17 @@ static int job_vector(void *p)
 	return out_vector(w->path, w->s, w->nMove, w->mvOrder, w->mvR, w->fPeriod);
 }
 
+typedef struct {
+	skidgpu_ctx **pctx;
+	const options *o;
+} create_job;
+
+static int job_create(void *p)
+{
+	const create_job *c = (const create_job *)p;
+	return skidgpu_create(c->pctx, c->o->iDevice, c->o->fPeriod, c->o->fCenter, c->o->bPeriodic, c->o->bOutDiag);
+}
+
 static double wall(void)
 {
 	struct timespec t;
@@ -252,8 +263,9 @@ int main(int argc, char **argv)
 	float fStep;
 	int nGroup = 1, nMove = 0, nIttr = 0, nUnbound = 0, nBefore = 0, nExtra = 0;
 	char achFile[300];
-	bg_job denJob = {0}, rayJob = {0};
+	bg_job denJob = {0}, rayJob = {0}, createJob = {0};
 	write_job denArgs, rayArgs;
+	create_job createArgs;
 	int *mvOrder = NULL;
 	float *mvR = NULL;
 	double t0 = wall(), tRead, tInit, tStages, tEnd; /* host wall clock, reported with SKID_HOST_TIMING=1 */
@@ -262,6 +274,10 @@ int main(int argc, char **argv)
 	parse_args(argc, argv, &o);
 	fStep = 0.5 * o.fCvg; /* main.c:345 */
 
+	/* the CUDA context comes up on a helper thread while stdin is being read and decoded */
+	createArgs.pctx = &ctx;
+	createArgs.o = &o;
+	bg_start(&createJob, job_create, &createArgs);
 	if (tipsy_read(stdin, o.bStandard, &s)) {
 		fprintf(stderr, "ERROR: could not read a TIPSY %s binary from stdin\n", o.bStandard ? "standard" : "native");
 		return 1;
@@ -270,7 +286,7 @@ int main(int argc, char **argv)
 	fflush(stdout);
 	tRead = wall();
 
-	if (skidgpu_create(&ctx, o.iDevice, o.fPeriod, o.fCenter, o.bPeriodic, o.bOutDiag)) die(NULL, "skidgpu_create");
+	if (bg_wait(&createJob)) die(NULL, "skidgpu_create");
 	if (skidgpu_set_particles(ctx, s.p, s.n, s.nGas, s.nDark, s.nStar)) die(ctx, "skidgpu_set_particles");
 	piGroup = (int *)calloc((size_t)s.n, sizeof(int));
 	rho = (float *)calloc((size_t)s.n, sizeof(float));
