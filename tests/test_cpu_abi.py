@@ -37,6 +37,14 @@ def test_struct_layouts():
     # PINIT 48 B, PGROUP 68 B (measured sizeof of kd.h:27-55)
     assert tipsy.PINIT_DTYPE.itemsize == 48 and tipsy.PINIT_DTYPE.fields["iOrder"][1] == 44
     assert tipsy.PGROUP_DTYPE.itemsize == 68 and tipsy.PGROUP_DTYPE.fields["nMembers"][1] == 56
+    # skidgpu_stat_row (include/skidgpu.h) == the ctypes mirror == the oracle's row: int + 10 floats
+    from oracle import orc
+    assert api.STAT_ROW_DTYPE.itemsize == 44 and api.STAT_ROW_DTYPE == orc.STAT_ROW_DTYPE
+    hdr = open(os.path.join(ROOT, "include", "skidgpu.h")).read()
+    body = re.search(r"typedef struct \{([^}]*)\} skidgpu_stat_row;", hdr).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [t for t in re.findall(r"\b(nMembers|f[A-Za-z0-9]+)\b", body) if t != "float"]
+    assert names == list(api.STAT_ROW_DTYPE.names), names
 
 
 def test_no_cpu_fallback(built):
