@@ -177,3 +177,25 @@ def test_stats_match_reference_stat_file(orc, demo_input, demo_golden):
     assert len(lines) == len(ref_lines) == 68
     same = sum(a.split()[:18] == b.split()[:18] for a, b in zip(lines, ref_lines))
     assert same == 68, [(a, b) for a, b in zip(lines, ref_lines) if a.split()[:18] != b.split()[:18]][:3]
+
+
+def test_stats_kernel_scheme_model(orc, demo_input, demo_golden):
+    """tools/stats_model.py restates the device kernel's scheme (radix-sort keys, chunks of 32 members, carried
+    float chains, ballot-style selections) in numpy; on the demo's 68 groups it is bit-identical to orc_stats."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import stats_model
+    from skid_b200.api import csmExp2Hub
+    p, ng, nd, ns, _ = demo_input
+    nGroup = 69
+    rc = np.zeros((nGroup, 3), np.float32)
+    vc = np.zeros((nGroup, 3), np.float32)
+    rc[1:], vc[1:] = demo_golden["gtp_pos"], demo_golden["gtp_vel"]
+    f32 = np.float32
+    dExpHub = csmExp2Hub(1.0, float(f32(DEMO["H0"])), 1.0, 0.0)
+    ref = orc.stats(p["r"], p["v"], p["fMass"], p["fSoft"], p["fTemp"], demo_golden["density"], ng, nd,
+                    demo_golden["grp"], nGroup, rc, vc, (1.0, 1.0, 1.0), 1.0, 0.0, dExpHub, 170.0, 3.4e38)
+    with np.errstate(all="ignore"):
+        mod = stats_model.model(p, demo_golden["density"], ng, nd, demo_golden["grp"], nGroup, rc, vc,
+                                np.array([0.5, 0.5, 0.5], f32), 1.0, f32(1.0), f32(dExpHub), f32(170.0), f32(3.4e38))
+    for f in ref.dtype.names:
+        assert np.array_equal(ref[f], mod[f]), f
