@@ -199,3 +199,28 @@ def test_stats_kernel_scheme_model(orc, demo_input, demo_golden):
                                 np.array([0.5, 0.5, 0.5], f32), 1.0, f32(1.0), f32(dExpHub), f32(170.0), f32(3.4e38))
     for f in ref.dtype.names:
         assert np.array_equal(ref[f], mod[f]), f
+
+
+SYNTH_CASES = {"dark13": ("dark", 1 << 13, 3), "gasdark13": ("gasdark", 1 << 13, 11), "massive14": ("massive", 1 << 14, 9)}
+
+
+@pytest.mark.parametrize("name", sorted(SYNTH_CASES))
+def test_oracle_pipeline_matches_reference_on_synthetic_boxes(orc, name):
+    """The whole stage script over the restatement (oracle/pipeline.py) against golden results of the unmodified
+    reference on synthetic boxes (tests/golden/synth_golden.npz, made by make_synth_golden.py): dark, gas+dark
+    (-gd, Lambda cosmology, no potential update after removals) and massive halos with a 4x linking length."""
+    from oracle import pipeline
+    from oracle.refdump import canonical_labels
+    from skid_b200 import synth
+    from skid_b200.api import csmExp2Hub
+    gold = np.load(os.path.join(GOLDEN, "synth_golden.npz"))
+    kind, n, seed = SYNTH_CASES[name]
+    snap = synth.make_box(n, seed=seed, kind=kind)
+    res = pipeline.run_port(snap, csmExp2Hub)
+    nIttr, nBefore, nUnbound, nGroup, _ = gold[name + "_log"]
+    assert abs(res["nIttr"] - nIttr) <= 1
+    assert res["nGroupBefore"] == nBefore
+    assert abs(res["nUnbound"] - nUnbound) <= max(2, nUnbound // 50)
+    assert abs(res["nGroup"] - nGroup) <= 1
+    same = np.mean(canonical_labels(gold[name + "_grp"].astype(np.int64)) == canonical_labels(res["grp"]))
+    assert same >= 0.999, same
