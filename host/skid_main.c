@@ -234,6 +234,31 @@ static int job_vector(void *p)
 	return out_vector(w->path, w->s, w->nMove, w->mvOrder, w->mvR, w->fPeriod);
 }
 
+static double wall(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return t.tv_sec + 1e-9 * t.tv_nsec;
+}
+
+/* lap timer for SKID_HOST_TIMING: wall time of every host-side phase, in call order */
+static struct {
+	const char *name[32];
+	double sec[32];
+	int n;
+	double last;
+} g_lap;
+
+static void lap(const char *name)
+{
+	const double t = wall();
+	if (g_lap.n < 32) {
+		g_lap.name[g_lap.n] = name;
+		g_lap.sec[g_lap.n++] = t - g_lap.last;
+	}
+	g_lap.last = t;
+}
+
 typedef struct {
 	skidgpu_ctx **pctx;
 	const options *o;
@@ -242,14 +267,13 @@ typedef struct {
 static int job_create(void *p)
 {
 	const create_job *c = (const create_job *)p;
-	return skidgpu_create(c->pctx, c->o->iDevice, c->o->fPeriod, c->o->fCenter, c->o->bPeriodic, c->o->bOutDiag);
-}
-
-static double wall(void)
-{
-	struct timespec t;
-	clock_gettime(CLOCK_MONOTONIC, &t);
-	return t.tv_sec + 1e-9 * t.tv_nsec;
+	int rc = skidgpu_create(c->pctx, c->o->iDevice, c->o->fPeriod, c->o->fCenter, c->o->bPeriodic, c->o->bOutDiag);
+	if (!rc && getenv("SKID_PREALLOC_GB")) { /* experiment: pool growth off the critical path */
+		double t = wall();
+		skidgpu_reserve(*c->pctx, (unsigned long long)(atof(getenv("SKID_PREALLOC_GB")) * 1073741824.0));
+		if (getenv("SKID_HOST_TIMING")) fprintf(stderr, "{\"reserve_s\": %.3f}\n", wall() - t);
+	}
+	return rc;
 }
 
 int main(int argc, char **argv)
@@ -270,6 +294,7 @@ int main(int argc, char **argv)
 	float *mvR = NULL;
 	double t0 = wall(), tRead, tInit, tStages, tEnd; /* host wall clock, reported with SKID_HOST_TIMING=1 */
 
+	g_lap.last = t0;
 	printf("SKID v1.4.1 (B200 GPU hot path): group finder compatible with SKID v1.4.1, Stadel 2000\n");
 	parse_args(argc, argv, &o);
 	fStep = 0.5 * o.fCvg; /* main.c:345 */
@@ -285,12 +310,15 @@ int main(int argc, char **argv)
 	printf("nDark:%d nGas:%d nStar:%d\n", s.nDark, s.nGas, s.nStar);
 	fflush(stdout);
 	tRead = wall();
+	lap("read_input");
 
 	if (bg_wait(&createJob)) die(NULL, "skidgpu_create");
+	lap("wait_context");
 	if (skidgpu_set_particles(ctx, s.p, s.n, s.nGas, s.nDark, s.nStar)) die(ctx, "skidgpu_set_particles");
 	piGroup = (int *)calloc((size_t)s.n, sizeof(int));
 	rho = (float *)calloc((size_t)s.n, sizeof(float));
 	tInit = wall();
+	lap("upload");
 
 	if (o.bUnbindOnly) {
 		/* main.c:349-373: strip a trailing .grp, read <name>.grp and, if present, <name>.gtp */
@@ -307,6 +335,7 @@ int main(int argc, char **argv)
 		if (skidgpu_set_groups(ctx, piGroup, nGroup, rc ? cat : NULL)) die(ctx, "skidgpu_set_groups");
 	} else {
 		if (skidgpu_density(ctx, o.nSmooth, o.bGasAndDark, o.bGasOnly, rho, NULL, &nExtra)) die(ctx, "skidgpu_density");
+		lap("density");
 		if (o.bPeriodic) printf("nExtraScat:%d\n", nExtra);
 		if (o.bOutDens) {
 			snprintf(denArgs.path, sizeof denArgs.path, "%s.den", o.achName);
@@ -317,13 +346,17 @@ int main(int argc, char **argv)
 		if (skidgpu_move(ctx, o.fDensMin, o.fTempMax, o.fMassMax, o.fCvg, fStep, o.bForceInitialCut, o.bNoPrune,
 		                 log_cb, NULL, &nMove, &nIttr))
 			die(ctx, "skidgpu_move");
+		lap("move");
 		if (skidgpu_fof(ctx, o.fTau, &nGroup)) die(ctx, "skidgpu_fof");
 		if (skidgpu_microstep(ctx, PRUNE_STEPS, MICRO_STEP * fStep, log_cb, NULL)) die(ctx, "skidgpu_microstep");
+		lap("fof_microstep");
 		if (o.bOutRay) {
 			mvOrder = (int *)malloc((size_t)(nMove ? nMove : 1) * sizeof(int));
 			mvR = (float *)malloc((size_t)(nMove ? nMove : 1) * 3 * sizeof(float));
 			if (skidgpu_get_moved(ctx, mvOrder, mvR)) die(ctx, "skidgpu_get_moved");
+			lap("get_moved");
 			bg_wait(&denJob); /* one set of writer threads at a time */
+			lap("wait_den_writer");
 			snprintf(rayArgs.path, sizeof rayArgs.path, "%s.ray", o.achName);
 			rayArgs.s = &s;
 			rayArgs.nMove = nMove;
@@ -334,6 +367,7 @@ int main(int argc, char **argv)
 		}
 		cat = (skidgpu_pgroup *)calloc((size_t)nGroup + 1, sizeof(skidgpu_pgroup));
 		if (skidgpu_centers(ctx, NULL, NULL)) die(ctx, "skidgpu_centers");
+		lap("centers");
 	}
 	/* kdSetUniverse / kdSetSoft / kdUnbind / kdTooSmall (main.c:459-471) */
 	if (o.bEps && skidgpu_set_soft(ctx, o.fEps)) die(ctx, "skidgpu_set_soft");
@@ -344,16 +378,19 @@ int main(int argc, char **argv)
 		if (skidgpu_unbind(ctx, o.G, o.z, fCosmo, o.iSoftType, o.fScoop, o.bNoUnbind, o.nMaxMembers, o.nMembers,
 		                   piGroup, cat, &nGroup, &nUnbound, &nBefore))
 			die(ctx, "skidgpu_unbind");
+		lap("unbind");
 		printf("Groups before Unbind:%d\n", nBefore);
 		printf("Number of particles Unbound:%d\n", nUnbound);
 		printf("Number of Groups:%d\n", nGroup - 1);
 		fflush(stdout);
 		tStages = wall();
 		if (bg_wait(&denJob) | bg_wait(&rayJob)) fprintf(stderr, "WARNING: could not write the .den/.ray file\n");
+		lap("wait_ray_writer");
 		snprintf(achFile, sizeof achFile, "%s.grp", o.achName);
 		out_group(achFile, s.n, piGroup);
 		snprintf(achFile, sizeof achFile, "%s.gtp", o.achName);
 		out_gtp(achFile, o.bStandard, s.time, nGroup, cat);
+		lap("write_grp_gtp");
 		if (o.bOutStats) {
 			/* kdOutStats, main.c:482-484 */
 			skidgpu_stat_row *rows = (skidgpu_stat_row *)calloc((size_t)nGroup + 1, sizeof(skidgpu_stat_row));
@@ -361,6 +398,7 @@ int main(int argc, char **argv)
 			snprintf(achFile, sizeof achFile, "%s.stat", o.achName);
 			out_stats(achFile, nGroup, cat, rows);
 			free(rows);
+			lap("stats");
 		}
 	}
 	printf("SKID GPU Time:\n");
@@ -373,11 +411,16 @@ int main(int argc, char **argv)
 	if (!o.bNoUnbind) print_time("   Unbinding:          ", skidgpu_stage_ms(ctx, 5));
 	fflush(stdout);
 	tEnd = wall();
-	if (getenv("SKID_HOST_TIMING"))
+	if (getenv("SKID_HOST_TIMING")) {
+		int k;
+		fprintf(stderr, "{\"host_laps_s\": {");
+		for (k = 0; k < g_lap.n; ++k) fprintf(stderr, "%s\"%s\": %.3f", k ? ", " : "", g_lap.name[k], g_lap.sec[k]);
+		fprintf(stderr, "}}\n");
 		fprintf(stderr,
 		        "{\"host_wall_s\": {\"read\": %.3f, \"create_upload\": %.3f, \"stages_with_overlapped_writers\": %.3f, "
 		        "\"final_writers\": %.3f, \"total\": %.3f}, \"n\": %d, \"threads\": %d}\n",
 		        tRead - t0, tInit - tRead, tStages - tInit, tEnd - tStages, tEnd - t0, s.n, host_threads());
+	}
 	skidgpu_destroy(ctx);
 	free(mvOrder);
 	free(mvR);

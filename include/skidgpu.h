@@ -69,6 +69,12 @@ int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPeriod[3],
 void skidgpu_destroy(skidgpu_ctx *ctx);
 const char *skidgpu_last_error(skidgpu_ctx *ctx);
 
+/* Optional hint (no reference equivalent): grow the context's device memory pool by `bytes` ahead of
+ * time, e.g. from a helper thread while the snapshot is still being read (the particle count is in the
+ * TIPSY header).  The hot path needs about 700 bytes per particle; a first pass otherwise pays for the
+ * pool growth on its critical path.  Clamped to half of the free device memory; never changes results. */
+int skidgpu_reserve(skidgpu_ctx *ctx, unsigned long long bytes);
+
 /* Multi-GPU sharding: this context owns movers/groups shard `rank` of `nranks`.
  * Default 0 of 1.  Scatterers and trees are always replicated. */
 int skidgpu_set_shard(skidgpu_ctx *ctx, int rank, int nranks);

@@ -32,7 +32,7 @@ _lib = None
 
 # every symbol include/skidgpu.h declares
 EXPORTS = [
-    "skidgpu_create", "skidgpu_destroy", "skidgpu_last_error", "skidgpu_set_shard", "skidgpu_set_particles",
+    "skidgpu_create", "skidgpu_destroy", "skidgpu_last_error", "skidgpu_reserve", "skidgpu_set_shard", "skidgpu_set_particles",
     "skidgpu_set_particles_dev", "skidgpu_set_soft", "skidgpu_density", "skidgpu_keep_neighbors",
     "skidgpu_get_neighbors", "skidgpu_move", "skidgpu_keep_step0", "skidgpu_get_step0", "skidgpu_fof",
     "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_moved_dev", "skidgpu_centers", "skidgpu_set_groups",
@@ -56,6 +56,7 @@ def load_library():
     lib.skidgpu_destroy.restype = None
     lib.skidgpu_last_error.argtypes = [vp]
     lib.skidgpu_last_error.restype = C.c_char_p
+    lib.skidgpu_reserve.argtypes = [vp, C.c_ulonglong]
     lib.skidgpu_set_shard.argtypes = [vp, i, i]
     lib.skidgpu_set_particles.argtypes = [vp, vp, i, i, i, i]
     lib.skidgpu_set_particles_dev.argtypes = [vp] + [vp] * 9 + [i, i, i, i]

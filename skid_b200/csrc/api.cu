@@ -67,6 +67,25 @@ extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPerio
 	return SKIDGPU_OK;
 }
 
+// Device memory comes from the stream-ordered pool, which grows on demand: on a first pass that growth (driver
+// allocation + mapping, ~11 GB at 2^24 particles) is host time on the critical path.  A caller that knows the
+// particle count early (the TIPSY header) can grow the pool ahead of time, e.g. while the records are still
+// being read: the block is allocated and freed at once and stays cached in the pool.
+extern "C" int skidgpu_reserve(skidgpu_ctx *ctx, unsigned long long bytes)
+{
+	API_BEGIN(ctx)
+	size_t freeB = 0, totalB = 0;
+	CK(cudaMemGetInfo(&freeB, &totalB));
+	if (bytes > freeB / 2) bytes = freeB / 2; // a hint, never a reason to fail
+	if (bytes > 0) {
+		void *p = nullptr;
+		CK(cudaMallocAsync(&p, (size_t)bytes, ctx->stream));
+		CK(cudaFreeAsync(p, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	API_END(ctx)
+}
+
 extern "C" void skidgpu_destroy(skidgpu_ctx *ctx)
 {
 	if (!ctx) return;

@@ -60,7 +60,7 @@ struct skidgpu_ctx {
 	float listInitFactor = 0.3f;
 	DevBuf<uint32_t> mQueue; // movers that refresh their list this step
 	// tiles: TILE consecutive entries of the position-sorted active list share one scatterer list (move.cu)
-	int nTiles = 0, tileStepsLeft = 0, tileWindow = 5, tileBuilds = 0;
+	int nTiles = 0, tileStepsLeft = 0, tileWindow = 5, tileBuilds = 0, superCap = 2048;
 	DevBuf<uint64_t> tKeys;
 	DevBuf<uint32_t> tList, tOff;
 	uint32_t bigBase = 0, nBig = 0;

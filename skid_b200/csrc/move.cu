@@ -184,8 +184,9 @@ struct StepArgs {
 	int *tCnt;       // per tile: list length, -1 = overflow (members walk the tree themselves)
 	uint32_t *tileQueue;      // tiles that build their list with their own walk
 	uint32_t *tileQueueCount; // = dT + 3
-	uint32_t *supList; // SUPER_CAP per supertile (scratch between k_super_walk and k_tile_filter)
+	uint32_t *supList; // supCap per supertile (scratch between k_super_walk and k_tile_filter)
 	int *supCnt;
+	int supCap;
 };
 
 // kdMoveParticles (kd.c:711-729) for one mover.  The reference forms ai = fStep/sqrt(|a|^2) in double and
@@ -409,6 +410,7 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 		}                                                                                      \
 	}
 constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
+constexpr int TILEWALK_OCC_DEFAULT = 4;
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
 {
@@ -464,7 +466,8 @@ __global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t 
 // `reachShort` (0: valid where the movers are now) and appended to `shortQueue`: it is then walked again
 // before EVERY step of the window (one_step launches this kernel on the short queue with reach < 0 =
 // "skip the first attempt").
-__global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a, const uint32_t *queue, const uint32_t *queueCount,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const uint32_t *queue, const uint32_t *queueCount,
                                                    float reach, float reachShort, uint32_t *shortQueue,
                                                    uint32_t *shortCount)
 {
@@ -571,7 +574,7 @@ __global__ void __launch_bounds__(128) k_tile_walk(const StepArgs a, const uint3
 //    tree walks, and the expensive test runs on ~1000 entries instead of ~6000.
 // Supertiles whose superset overflows (members far apart) fall back to tile_walk in k_tile_filter.
 constexpr int SUPER = 32 / TILE;
-constexpr int SUPER_CAP = 2048;
+constexpr int SUPER_CAP = 2048; // default superset capacity per supertile (ctx.superCap, SKIDGPU_SUPER_CAP)
 __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper, float reach)
 {
 	const int lane = threadIdx.x & 31;
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper
 	                                                 fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(z0), fabsf(z1))));
 	const float r2 = r * r;
 	if (mi < a.nActive) a.tPos[mi] = make_float4(x, y, z, r);
-	uint32_t *sup = a.supList + (size_t)st * SUPER_CAP;
+	uint32_t *sup = a.supList + (size_t)st * a.supCap;
 	int ns = 0;
 	bool overflow = false;
 	int lev = a.tv.top - 1;
@@ -623,7 +626,7 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper
 		if (cand) cand = a.entNR[e_].z >= T; /* dead scatterers never come back */             \
 		const uint32_t cm = __ballot_sync(SK_FULL, cand);                                      \
 		const int nc = __popc(cm);                                                             \
-		if (ns + nc > SUPER_CAP) overflow = true;                                              \
+		if (ns + nc > a.supCap) overflow = true;                                               \
 		else if (cand) sup[ns + __popc(cm & lt)] = e_;                                         \
 		ns += nc;                                                                              \
 	}
@@ -675,7 +678,7 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	const float T = __uint_as_float(a.dT[0]);
 	const int st = t / SUPER;
 	const int ns = a.supCnt[st];
-	const uint32_t *sup = a.supList + (size_t)st * SUPER_CAP;
+	const uint32_t *sup = a.supList + (size_t)st * a.supCap;
 	const float r = a.tPos[t * TILE].w;
 	if (ns < 0) { // the supertile's members are far apart: own walk (k_tile_walk)
 		if (lane == 0) a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
@@ -1121,6 +1124,7 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tileQueue = c.tileQueue.p;
 	sa.tileQueueCount = c.dT.p ? c.dT.p + 3 : nullptr;
 	sa.supCnt = c.supCnt.p;
+	sa.supCap = c.superCap;
 }
 
 static int count_scatterers(skidgpu_ctx &c)
@@ -1156,6 +1160,21 @@ static int move_kernel()
 	return v;
 }
 
+// k_tile_walk is latency bound (dependent tree loads): resident blocks per SM = SKIDGPU_TILEWALK_OCC (4, 6 or 8;
+// the register budget follows from the launch bounds), persistent grid of that many blocks per SM.
+static void launch_tile_walk(skidgpu_ctx &c, const StepArgs &sa, const uint32_t *queue, const uint32_t *queueCount,
+                             float reach, float reachShort, uint32_t *shortQueue, uint32_t *shortCount)
+{
+	int occ = TILEWALK_OCC_DEFAULT;
+	if (const char *e = getenv("SKIDGPU_TILEWALK_OCC")) occ = atoi(e);
+	if (occ >= 8)
+		SK_LAUNCH(k_tile_walk<8>, 148 * 8, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
+	else if (occ >= 6)
+		SK_LAUNCH(k_tile_walk<6>, 148 * 6, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
+	else
+		SK_LAUNCH(k_tile_walk<4>, 148 * 4, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
+}
+
 // Sort the active movers by position and build the tile lists; valid for `steps` steps of length fStep.
 static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 {
@@ -1166,11 +1185,8 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	// The active list starts in Morton order of the initial positions and compaction keeps its order, so
 	// tiles stay compact for a while: re-sort by current position only every few rebuilds (the lists are
 	// unions of per-member neighbourhoods - compactness is efficiency, never correctness).
-	static int every = -1;
-	if (every < 0) {
-		const char *e = getenv("SKIDGPU_TILE_SORT_EVERY");
-		every = e ? atoi(e) : 4;
-	}
+	int every = 4;
+	if (const char *e = getenv("SKIDGPU_TILE_SORT_EVERY")) every = atoi(e);
 	if (every > 0 && c.tileBuilds % every == every - 1) {
 		uint64_t *keys = c.tKeys.alloc(c.nActive);
 		SK_LAUNCH(k_mover_keys, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
@@ -1190,8 +1206,7 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, reach);
 	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
 	// spread-out supertiles build per tile; tiles whose 5-step list overflows become short tiles (dT[5])
-	SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, s, sa, sa.tileQueue, sa.tileQueueCount, reach,
-	          steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
+	launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
 	c.tileFresh = true;
 	if (getenv("SKIDGPU_TILE_DIAG")) {
 		std::vector<int> h(c.nTiles);
@@ -1221,7 +1236,11 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 			if (v < 0) ++sover;
 			else ssum += v;
 		}
-		fprintf(stderr, "supertiles: n=%d overflow=%d mean=%.1f\n", nSuper, sover, nSuper > sover ? (double)ssum / (nSuper - sover) : 0.0);
+		uint32_t hq[8];
+		CK(cudaMemcpyAsync(hq, c.dT.p, sizeof hq, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		fprintf(stderr, "supertiles: n=%d overflow=%d mean=%.1f cap=%d | walked tiles=%u short tiles=%u big slots=%u/%u\n", nSuper,
+		        sover, nSuper > sover ? (double)ssum / (nSuper - sover) : 0.0, c.superCap, hq[3], hq[5], hq[6], c.nBig);
 	}
 }
 
@@ -1237,8 +1256,7 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 			if (c.tileStepsLeft <= 0) rebuild_tiles(c, sa, c.tileWindow);
 			--c.tileStepsLeft;
 			if (!c.tileFresh) // short tiles are rebuilt before every step (their list has no reach)
-				SK_LAUNCH(k_tile_walk, AUX_BLOCKS, 128, 0, c.stream, sa, c.shortQueue.p, c.dT.p + 5, -1.0f, 0.0f,
-				          (uint32_t *)nullptr, (uint32_t *)nullptr);
+				launch_tile_walk(c, sa, c.shortQueue.p, c.dT.p + 5, -1.0f, 0.0f, nullptr, nullptr);
 			c.tileFresh = false;
 			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa);
 			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, c.stream, sa, sa.queue, 0, sa.queueCount);
@@ -1326,7 +1344,9 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 			c.tOff.alloc(nt);
 			c.tPos.alloc(nt * TILE);
 			c.tCnt.alloc(nt);
-			c.supList.alloc(ceil_div(nt, SUPER) * SUPER_CAP);
+			c.superCap = SUPER_CAP;
+			if (const char *e = getenv("SKIDGPU_SUPER_CAP")) c.superCap = std::max(256, atoi(e)) & ~31;
+			c.supList.alloc(ceil_div(nt, SUPER) * (size_t)c.superCap);
 			c.supCnt.alloc(ceil_div(nt, SUPER));
 			c.tileQueue.alloc(nt);
 			c.shortQueue.alloc(nt);
