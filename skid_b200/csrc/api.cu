@@ -147,6 +147,16 @@ static void set_counts(skidgpu_ctx *c, int n, int nGas, int nDark, int nStar)
 	c->nGroup = 0;
 	c->nEnt = c->nExtra = c->nAct = 0;
 	c->haveCenters = false;
+	if (n > c->reservedFor) { // first pass at this size: grow the pool in one piece, not buffer by buffer
+		size_t freeB = 0, totalB = 0;
+		unsigned long long want = 700ull * (unsigned long long)n; // measured footprint of the hot path, DESIGN.md 3
+		CK(cudaMemGetInfo(&freeB, &totalB));
+		if (want > freeB / 2) want = freeB / 2;
+		void *p = nullptr;
+		if (want > 0 && cudaMallocAsync(&p, (size_t)want, c->stream) == cudaSuccess) CK(cudaFreeAsync(p, c->stream));
+		else (void)cudaGetLastError();
+		c->reservedFor = n;
+	}
 	c->x.alloc(n);
 	c->y.alloc(n);
 	c->z.alloc(n);
@@ -288,32 +298,49 @@ extern "C" int skidgpu_microstep(skidgpu_ctx *ctx, int nSteps, float fStep, skid
 	API_END(ctx)
 }
 
+// Movers live in Morton order on the device; kdOutVector wants them in ascending iOrder (kd.c:1561).  A mover's
+// output slot is the number of movers with a smaller iOrder: mark, scan, scatter - all on the device, then two
+// contiguous copies straight into the caller's arrays (a host-side index sort cost 1.4 s at 8.3 M movers).
+__global__ void __launch_bounds__(256) k_mark_movers(int m, const int *mOrd, uint32_t *flags)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j < m) flags[mOrd[j]] = 1u;
+}
+
+__global__ void __launch_bounds__(256)
+    k_pack_moved(int m, const int *mOrd, const uint32_t *pos, const float *mx, const float *my, const float *mz,
+                 int *outOrd, float *outR3)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= m) return;
+	const int o = mOrd[j];
+	const size_t i = pos[o];
+	outOrd[i] = o;
+	outR3[3 * i] = mx[j];
+	outR3[3 * i + 1] = my[j];
+	outR3[3 * i + 2] = mz[j];
+}
+
 extern "C" int skidgpu_get_moved(skidgpu_ctx *ctx, int *iOrder, float *r3)
 {
 	API_BEGIN(ctx)
-	const int m = ctx->nMove;
+	const int m = ctx->nMove, n = ctx->n;
 	if (m > 0) {
-		std::vector<float> hx(m), hy(m), hz(m);
-		std::vector<int> ord(m);
 		cudaStream_t s = ctx->stream;
-		CK(cudaMemcpyAsync(ord.data(), ctx->mOrd.p, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
-		CK(cudaMemcpyAsync(hx.data(), ctx->mx.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-		CK(cudaMemcpyAsync(hy.data(), ctx->my.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-		CK(cudaMemcpyAsync(hz.data(), ctx->mz.p, sizeof(float) * m, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-		// movers live in Morton order on the device; kdOutVector wants iOrder order (kd.c:1561)
-		std::vector<int> idx(m);
-		for (int i = 0; i < m; ++i) idx[i] = i;
-		std::sort(idx.begin(), idx.end(), [&](int a, int b) { return ord[a] < ord[b]; });
-		for (int i = 0; i < m; ++i) {
-			int j = idx[i];
-			if (iOrder) iOrder[i] = ord[j];
-			if (r3) {
-				r3[3 * i] = hx[j];
-				r3[3 * i + 1] = hy[j];
-				r3[3 * i + 2] = hz[j];
-			}
-		}
+		DevBuf<int> dOrd;
+		DevBuf<float> dR3;
+		uint32_t *flags = ctx->flags.alloc((size_t)n + 1);
+		uint32_t *scan = ctx->scan.alloc((size_t)n + 64);
+		dOrd.alloc(m);
+		dR3.alloc((size_t)3 * m);
+		CK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * ((size_t)n + 1), s));
+		SK_LAUNCH(k_mark_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, ctx->mOrd.p, flags);
+		exclusive_scan_u32(flags, scan, n, ctx->ws, s);
+		SK_LAUNCH(k_pack_moved, (unsigned)ceil_div(m, 256), 256, 0, s, m, ctx->mOrd.p, scan, ctx->mx.p, ctx->my.p,
+		          ctx->mz.p, dOrd.p, dR3.p);
+		if (iOrder) CK(cudaMemcpyAsync(iOrder, dOrd.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, s));
+		if (r3) CK(cudaMemcpyAsync(r3, dR3.p, sizeof(float) * 3 * (size_t)m, cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s)); // before the local buffers are released
 	}
 	API_END(ctx)
 }

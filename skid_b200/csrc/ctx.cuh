@@ -15,6 +15,7 @@ struct skidgpu_ctx {
 
 	// ---- particles, SoA by iOrder (file order: gas, dark, star; kd.c:113-119)
 	int n = 0, nGas = 0, nDark = 0, nStar = 0, inType = 0;
+	int reservedFor = 0; // largest particle count the memory pool was pre-grown for (api.cu set_counts)
 	DevBuf<float> x, y, z, vx, vy, vz, mass, soft, temp;
 	DevBuf<float> rho, ball2; // by iOrder; 0 for non scatter-active
 	DevBuf<skidgpu_pinit> aos; // staging for the AoS upload

@@ -187,6 +187,7 @@ struct StepArgs {
 	uint32_t *supList; // supCap per supertile (scratch between k_super_walk and k_tile_filter)
 	int *supCnt;
 	int supCap;
+	int walkDyn; // k_tile_walk takes its tiles from a ticket counter (dT[7]) instead of a static round-robin
 };
 
 // kdMoveParticles (kd.c:711-729) for one mover.  The reference forms ai = fStep/sqrt(|a|^2) in double and
@@ -410,7 +411,8 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 		}                                                                                      \
 	}
 constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
-constexpr int TILEWALK_OCC_DEFAULT = 4;
+constexpr int TILEWALK_DYN_DEFAULT = 0;
+constexpr int TILEWALK_OCC_DEFAULT = 6; // measured (tools/ab_probe.py, 2^24): move 300 -> 291 ms gas+dark, 257 -> 230 ms massive
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
 {
@@ -475,8 +477,19 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint32_t nq = *queueCount;
 	const float T = __uint_as_float(a.dT[0]);
-	for (uint32_t wi = blockIdx.x * 4 + (threadIdx.x >> 5); wi < nq; wi += gridDim.x * 4) {
+	// the queued tiles differ a lot in cost (dense cores): with walkDyn a warp draws its next tile from a ticket
+	// counter (reset by k_update_T at the end of every step; one launch of this kernel per step)
+	uint32_t wi = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (a.walkDyn) {
+		if (lane == 0) wi = atomicAdd(a.dT + 7, 1u);
+		wi = __shfl_sync(SK_FULL, wi, 0);
+	}
+	for (; wi < nq;) {
 		const int t = (int)queue[wi];
+		if (a.walkDyn) {
+			if (lane == 0) wi = atomicAdd(a.dT + 7, 1u);
+			wi = __shfl_sync(SK_FULL, wi, 0);
+		} else wi += gridDim.x * 4;
 		uint32_t off = (uint32_t)t * TILE_CAP;
 		uint32_t *list = a.tList + off;
 		int cap = TILE_CAP;
@@ -979,6 +992,7 @@ __global__ void k_update_T(uint32_t *dT, int bNoPrune)
 	dT[2] = 0u; // refresh queues of the next step: movers, buckets, tree-walk movers
 	dT[3] = 0u;
 	dT[4] = 0u;
+	dT[7] = 0u; // ticket counter of k_tile_walk
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
@@ -1125,6 +1139,8 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tileQueueCount = c.dT.p ? c.dT.p + 3 : nullptr;
 	sa.supCnt = c.supCnt.p;
 	sa.supCap = c.superCap;
+	sa.walkDyn = TILEWALK_DYN_DEFAULT;
+	if (const char *e = getenv("SKIDGPU_TILEWALK_DYN")) sa.walkDyn = atoi(e);
 }
 
 static int count_scatterers(skidgpu_ctx &c)
@@ -1171,6 +1187,8 @@ static void launch_tile_walk(skidgpu_ctx &c, const StepArgs &sa, const uint32_t 
 		SK_LAUNCH(k_tile_walk<8>, 148 * 8, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
 	else if (occ >= 6)
 		SK_LAUNCH(k_tile_walk<6>, 148 * 6, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
+	else if (occ == 5)
+		SK_LAUNCH(k_tile_walk<5>, 148 * 5, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
 	else
 		SK_LAUNCH(k_tile_walk<4>, 148 * 4, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
 }
@@ -1304,7 +1322,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.haveCenters = false;
 	const int m = c.nMove;
 	uint32_t *dT = c.dT.alloc(8);
-	uint32_t initT[7] = {0u, T_NONE, 0u, 0u, 0u, 0u, 0u}; // threshold, running min of this step, refresh-queue lengths
+	uint32_t initT[8] = {0u, T_NONE, 0u, 0u, 0u, 0u, 0u, 0u}; // threshold, running min of this step, queue lengths, ticket
 	CK(cudaMemcpyAsync(dT, initT, sizeof initT, cudaMemcpyHostToDevice, s));
 	c.shardLo = (int)((long long)m * c.rank / c.nranks);
 	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
