@@ -47,6 +47,9 @@ extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPerio
 		c->bPeriodic = bPeriodic;
 		c->bDiag = bDiag;
 		CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&c->evWalk0, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&c->evWalk1, cudaEventDisableTiming));
 		{ // keep freed blocks cached in the stream-ordered pool (DevBuf, common.cuh)
 			cudaMemPool_t pool;
 			unsigned long long keep = ~0ull;
@@ -95,6 +98,12 @@ extern "C" void skidgpu_destroy(skidgpu_ctx *ctx)
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
 	if (ctx->evk0) cudaEventDestroy(ctx->evk0);
 	if (ctx->evk1) cudaEventDestroy(ctx->evk1);
+	if (ctx->evWalk0) cudaEventDestroy(ctx->evWalk0);
+	if (ctx->evWalk1) cudaEventDestroy(ctx->evWalk1);
+	if (ctx->stream2) {
+		cudaStreamSynchronize(ctx->stream2);
+		cudaStreamDestroy(ctx->stream2);
+	}
 	cudaStream_t s = ctx->stream;
 	g_skid_stream = s;
 	delete ctx; // DevBuf destructors free on s

@@ -67,6 +67,10 @@ struct skidgpu_ctx {
 	uint32_t bigBase = 0, nBig = 0;
 	DevBuf<float4> tPos;
 	DevBuf<int> tCnt;
+	DevBuf<uint8_t> tPend;
+	int tileOverlap = 0;
+	cudaStream_t stream2 = 0; // k_tile_walk beside k_tile_step at a rebuild step (move.cu)
+	cudaEvent_t evWalk0 = nullptr, evWalk1 = nullptr;
 	DevBuf<uint32_t> supList;
 	DevBuf<int> supCnt;
 	DevBuf<uint32_t> tileQueue, shortQueue;

@@ -187,6 +187,7 @@ struct StepArgs {
 	uint32_t *supList; // supCap per supertile (scratch between k_super_walk and k_tile_filter)
 	int *supCnt;
 	int supCap;
+	uint8_t *tPend; // per tile: 1 = queued for k_tile_walk at this rebuild (k_tile_filter)
 	int walkDyn; // k_tile_walk takes its tiles from a ticket counter (dT[7]) instead of a static round-robin
 };
 
@@ -411,8 +412,9 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 		}                                                                                      \
 	}
 constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
-constexpr int TILEWALK_DYN_DEFAULT = 0;
-constexpr int TILEWALK_OCC_DEFAULT = 6; // measured (tools/ab_probe.py, 2^24): move 300 -> 291 ms gas+dark, 257 -> 230 ms massive
+constexpr int TILEWALK_DYN_DEFAULT = 1; // measured with OCC 8: move 292 -> 288 ms gas+dark, 231 -> 215 ms massive
+constexpr int TILE_OVERLAP_DEFAULT = 0;
+constexpr int TILEWALK_OCC_DEFAULT = 8; // measured (tools/ab_probe.py, 2^24): move 300 -> 291 ms gas+dark, 257 -> 230 ms massive
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
 {
@@ -694,7 +696,10 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	const uint32_t *sup = a.supList + (size_t)st * a.supCap;
 	const float r = a.tPos[t * TILE].w;
 	if (ns < 0) { // the supertile's members are far apart: own walk (k_tile_walk)
-		if (lane == 0) a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
+		if (lane == 0) {
+			a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
+			a.tPend[t] = 1;
+		}
 		return;
 	}
 	uint32_t eN = ns > 0 ? sup[min(lane, ns - 1)] : 0u;
@@ -721,13 +726,17 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 			TILE_APPEND(cand, e);
 		}
 		if (overflow) { // too long for the window's reach: k_tile_walk retries and falls back to a zero-reach list
-			if (lane == 0) a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
+			if (lane == 0) {
+				a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
+				a.tPend[t] = 1;
+			}
 			return;
 		}
 	}
 	if (lane == 0) {
 		a.tCnt[t] = cnt;
 		a.tOff[t] = off;
+		a.tPend[t] = 0;
 	}
 }
 
@@ -745,12 +754,9 @@ struct TileShared {
 	float4 q[TILE_CHUNK]; // (4/fBall2, fNorm, rho, 0)
 };
 
-__global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
+__device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, TileShared &sh, uint32_t *sh_e)
 {
-	__shared__ TileShared sh;
-	__shared__ uint32_t sh_e[TILE_CHUNK];
 	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
-	const int t = blockIdx.x;
 	const int cnt = a.tCnt[t];
 	const int mi = t * TILE + m;
 	const bool have = mi < a.nActive;
@@ -804,6 +810,28 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
 		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
 	}
 	if (run && j == 0) finish_mover(a, id, x, y, z, ax, ay, az, rmin);
+}
+
+// One block per tile.  At a rebuild step the tiles that build their list with their own walk (k_tile_walk, a
+// latency-bound kernel over the few per cent of tiles in dense cores) are still being built on a second
+// stream: the first launch skips them (skip[t] != 0, written by k_tile_filter), a second, queue-driven launch
+// (persistent grid, tiles taken from `queue`) serves them once the walk has finished.
+__global__ void __launch_bounds__(TILE_THREADS)
+    k_tile_step(const StepArgs a, const uint8_t *skip, const uint32_t *queue, const uint32_t *queueCount)
+{
+	__shared__ TileShared sh;
+	__shared__ uint32_t sh_e[TILE_CHUNK];
+	if (queue) {
+		const uint32_t nq = *queueCount;
+		for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+			if (q != blockIdx.x) __syncthreads(); // the previous tile's staging buffers are still being read
+			tile_step_body(a, (int)queue[q], sh, sh_e);
+		}
+		return;
+	}
+	const int t = blockIdx.x;
+	if (skip && skip[t]) return;
+	tile_step_body(a, t, sh, sh_e);
 }
 
 // v1 kernel: one warp per mover walks the scatterer tree every step (profiles/r01_v1_move_*: issue
@@ -1139,6 +1167,7 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tileQueueCount = c.dT.p ? c.dT.p + 3 : nullptr;
 	sa.supCnt = c.supCnt.p;
 	sa.supCap = c.superCap;
+	sa.tPend = c.tPend.p;
 	sa.walkDyn = TILEWALK_DYN_DEFAULT;
 	if (const char *e = getenv("SKIDGPU_TILEWALK_DYN")) sa.walkDyn = atoi(e);
 }
@@ -1224,7 +1253,17 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, reach);
 	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
 	// spread-out supertiles build per tile; tiles whose 5-step list overflows become short tiles (dT[5])
-	launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
+	c.tileOverlap = TILE_OVERLAP_DEFAULT;
+	if (const char *e = getenv("SKIDGPU_TILE_OVERLAP")) c.tileOverlap = atoi(e);
+	if (c.tileOverlap) { // the walk of the queued tiles runs beside the step of all the others (one_step)
+		CK(cudaEventRecord(c.evWalk0, s));
+		CK(cudaStreamWaitEvent(c.stream2, c.evWalk0, 0));
+		std::swap(c.stream, c.stream2);
+		launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
+		std::swap(c.stream, c.stream2);
+		CK(cudaEventRecord(c.evWalk1, c.stream2));
+	} else
+		launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
 	c.tileFresh = true;
 	if (getenv("SKIDGPU_TILE_DIAG")) {
 		std::vector<int> h(c.nTiles);
@@ -1275,8 +1314,17 @@ static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 			--c.tileStepsLeft;
 			if (!c.tileFresh) // short tiles are rebuilt before every step (their list has no reach)
 				launch_tile_walk(c, sa, c.shortQueue.p, c.dT.p + 5, -1.0f, 0.0f, nullptr, nullptr);
+			const bool overlapped = c.tileFresh && c.tileOverlap;
 			c.tileFresh = false;
-			SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa);
+			if (overlapped) {
+				SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa, sa.tPend, (const uint32_t *)nullptr,
+				          (const uint32_t *)nullptr);
+				CK(cudaStreamWaitEvent(c.stream, c.evWalk1, 0));
+				SK_LAUNCH(k_tile_step, 148 * 16, TILE_THREADS, 0, c.stream, sa, (const uint8_t *)nullptr, sa.tileQueue,
+				          sa.tileQueueCount);
+			} else
+				SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa, (const uint8_t *)nullptr,
+				          (const uint32_t *)nullptr, (const uint32_t *)nullptr);
 			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, c.stream, sa, sa.queue, 0, sa.queueCount);
 		} else if (mk == MOVE_LIST) {
 			SK_LAUNCH(k_list_eval, (unsigned)ceil_div(c.nActive, EVAL_WARPS), EVAL_WARPS * 32, 0, c.stream, sa);
@@ -1362,6 +1410,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 			c.tOff.alloc(nt);
 			c.tPos.alloc(nt * TILE);
 			c.tCnt.alloc(nt);
+			c.tPend.alloc(nt);
 			c.superCap = SUPER_CAP;
 			if (const char *e = getenv("SKIDGPU_SUPER_CAP")) c.superCap = std::max(256, atoi(e)) & ~31;
 			c.supList.alloc(ceil_div(nt, SUPER) * (size_t)c.superCap);
