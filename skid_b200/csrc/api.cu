@@ -158,7 +158,9 @@ static void set_counts(skidgpu_ctx *c, int n, int nGas, int nDark, int nStar)
 	c->haveCenters = false;
 	if (n > c->reservedFor) { // first pass at this size: grow the pool in one piece, not buffer by buffer
 		size_t freeB = 0, totalB = 0;
-		unsigned long long want = 700ull * (unsigned long long)n; // measured footprint of the hot path, DESIGN.md 3
+		// measured footprint of the hot path: ~250 B/particle replicated (input, trees, scatterers)
+		// + ~450 B/particle for movers and tile lists, which are sharded across ranks
+		unsigned long long want = (250ull + 450ull / (unsigned long long)c->nranks) * (unsigned long long)n;
 		CK(cudaMemGetInfo(&freeB, &totalB));
 		if (want > freeB / 2) want = freeB / 2;
 		void *p = nullptr;
