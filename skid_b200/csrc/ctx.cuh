@@ -54,7 +54,6 @@ struct skidgpu_ctx {
 	long long moverSteps = 0;
 	DevBuf<float> mx, my, mz, rox, roy, roz;
 	DevBuf<int> mOrd; // mover id -> iOrder
-	DevBuf<uint8_t> mDead; // mover id -> converged at a prune inside a tile window (move.cu k_prune_mark)
 	DevBuf<uint32_t> actList, actList2;
 	DevBuf<uint32_t> mList;            // candidate lists, LIST_CAP per mover (move.cu)
 	DevBuf<float> lx0, ly0, lz0, ldelta, lhmin;

@@ -188,7 +188,6 @@ struct StepArgs {
 	int *supCnt;
 	int supCap;
 	uint8_t *tPend; // per tile: 1 = queued for k_tile_walk at this rebuild (k_tile_filter)
-	const uint8_t *dead; // per mover: converged at a prune INSIDE a tile window (still a slot of its tile, no longer moved)
 	int walkDyn; // k_tile_walk takes its tiles from a ticket counter (dT[7]) instead of a static round-robin
 };
 
@@ -415,7 +414,6 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
 constexpr int TILEWALK_DYN_DEFAULT = 1; // measured with OCC 8: move 292 -> 288 ms gas+dark, 231 -> 215 ms massive
 constexpr int TILE_OVERLAP_DEFAULT = 0;
-constexpr int TILE_WINDOW_DEFAULT = 5;
 constexpr int TILEWALK_OCC_DEFAULT = 8; // measured (tools/ab_probe.py, 2^24): move 300 -> 291 ms gas+dark, 257 -> 230 ms massive
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
@@ -761,9 +759,8 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
 	const int cnt = a.tCnt[t];
 	const int mi = t * TILE + m;
-	bool have = mi < a.nActive;
+	const bool have = mi < a.nActive;
 	const uint32_t id = have ? a.act[mi] : 0u;
-	if (have && a.dead[id]) have = false;
 	float x = 0.0f, y = 0.0f, z = 0.0f;
 	if (have) x = a.mx[id], y = a.my[id], z = a.mz[id];
 	const float T = __uint_as_float(a.dT[0]);
@@ -1105,26 +1102,6 @@ __global__ void __launch_bounds__(256)
 	roz[id] = mz[id];
 }
 
-// A prune that falls inside a tile window (SKIDGPU_TILE_WINDOW = 10: the lists span two blocks of 5 steps):
-// the tiles keep their slots, converged movers are only marked.  A marked mover does not move any more, so the
-// next full prune finds its displacement since rOld below fCvg again and drops it from the compacted list.
-__global__ void __launch_bounds__(256)
-    k_prune_mark(int nActive, const uint32_t *act, const uint32_t *flags, const float *mx, const float *my,
-                 const float *mz, float *rox, float *roy, float *roz, uint8_t *dead)
-{
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= nActive) return;
-	uint32_t id = act[i];
-	if (!flags[i]) {
-		dead[id] = 1;
-		return;
-	}
-	if (dead[id]) return; // cannot happen (a marked mover never moves), kept for safety
-	rox[id] = mx[id];
-	roy[id] = my[id];
-	roz[id] = mz[id];
-}
-
 static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 {
 	sa.tv = tree_view(c.treeE);
@@ -1191,7 +1168,6 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.supCnt = c.supCnt.p;
 	sa.supCap = c.superCap;
 	sa.tPend = c.tPend.p;
-	sa.dead = c.mDead.p;
 	sa.walkDyn = TILEWALK_DYN_DEFAULT;
 	if (const char *e = getenv("SKIDGPU_TILEWALK_DYN")) sa.walkDyn = atoi(e);
 }
@@ -1417,7 +1393,6 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.roy.alloc(m);
 		c.roz.alloc(m);
 		c.mOrd.alloc(m);
-		CK(cudaMemsetAsync(c.mDead.alloc(m), 0, m, s));
 		c.lx0.alloc(m);
 		c.ly0.alloc(m);
 		c.lz0.alloc(m);
@@ -1477,9 +1452,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.tileWindow = 1; // step 0 is followed by the initial cut and the log line; the blocks of 5 start after it
 	kt.stop(one_step(c, sa, bNoPrune));
 	c.tileStepsLeft = 0;
-	c.tileWindow = TILE_WINDOW_DEFAULT; // 5 = one prune block; 10 = the lists span two blocks (k_prune_mark)
-	if (const char *e = getenv("SKIDGPU_TILE_WINDOW")) c.tileWindow = atoi(e) >= 10 ? 10 : 5;
-	if (move_kernel() != MOVE_TILE) c.tileWindow = 5;
+	c.tileWindow = 5;
 	if (bInitial && c.nEnt > 0) sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
 	if (bInitial && c.nEnt > 0)
 		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p);
@@ -1510,17 +1483,13 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		return (long long)h;
 	};
 	long long nGlobal = global_active(c.nActive);
-	int nLive = c.nActive; // active movers; < c.nActive (slots of the tile lists) after a mid-window prune
 	while (nGlobal) {
 		int nl = 0;
 		kt.start();
 		const double ms0 = c.kernel_ms[0];
 		const int na0 = c.nActive;
 		for (int i = 0; i < 5; ++i) nl += one_step(c, sa, bNoPrune);
-		c.moverSteps -= 5ll * (c.nActive - nLive); // one_step counts slots; marked movers take no step
 		kt.stop(nl);
-		// a prune inside a tile window marks instead of compacting (the window is 10 steps and 5 are left)
-		const bool midWindow = move_kernel() == MOVE_TILE && c.tileStepsLeft > 0 && c.nActive > 0;
 		if (getenv("SKIDGPU_STEP_TRACE") && c.rank == 0)
 			fprintf(stderr, "ittr %d nActive %d ms5 %.3f\n", nIttr, na0, c.kernel_ms[0] - ms0);
 		// kdPruneInactive
@@ -1531,26 +1500,16 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 			SK_LAUNCH(k_prune_flags, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
 			          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, hx, hy, hz, fCvg2, pf);
 			exclusive_scan_u32(pf, ps, c.nActive, c.ws, s);
-			if (midWindow)
-				SK_LAUNCH(k_prune_mark, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, c.mx.p,
-				          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mDead.p);
-			else
-				SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, ps,
-				          c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p);
+			SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, ps,
+			          c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p);
 			CK(cudaMemcpyAsync(&na, ps + c.nActive, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 		}
 		nScat = count_scatterers(c); // synchronises
-		if (midWindow) {
-			nLive = (int)na; // the tiles keep their slots until the window ends
-		} else {
-			c.nActive = (int)na;
-			nLive = c.nActive;
-			std::swap(c.actList.p, c.actList2.p);
-			std::swap(c.actList.cap, c.actList2.cap);
-			c.tileStepsLeft = 0; // the active list changed: new tiles
-		}
-		nGlobal = global_active(nLive);
-		if (nGlobal == 0) c.nActive = 0;
+		c.nActive = (int)na;
+		std::swap(c.actList.p, c.actList2.p);
+		std::swap(c.actList.cap, c.actList2.cap);
+		c.tileStepsLeft = 0; // the active list changed: new tiles
+		nGlobal = global_active(c.nActive);
 		if (cb) cb(user, 0, nIttr, (int)nGlobal, nScat);
 		++nIttr;
 	}
@@ -1565,7 +1524,6 @@ void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb,
 	// kdReactivateMove (kd.c:796-799)
 	c.nActive = c.nOwned;
 	init_active_list(c);
-	if (c.nMove > 0) CK(cudaMemsetAsync(c.mDead.p, 0, c.nMove, s));
 	c.tileStepsLeft = 0;
 	c.tileWindow = nSteps > 0 ? nSteps : 1;
 	StepArgs sa;

@@ -1,5 +1,10 @@
 mkdir -p gpurun_out
-(timeout 60 python -m pytest tests/test_gpu_demo.py tests/test_gpu_synth_golden.py tests/test_gpu_move_kernels.py tests/test_gpu_properties.py -m gpu -q -p no:cacheprovider 2>&1 | tail -2) 
-(SKIDGPU_TILE_WINDOW=10 timeout 30 python -m pytest tests/test_gpu_demo.py tests/test_gpu_synth_golden.py -m gpu -q -p no:cacheprovider 2>&1 | tail -2)
-timeout 60 python tools/ab_probe.py --log2n 24 --kind gasdark --passes 2 "" "SKIDGPU_TILE_WINDOW=10" > gpurun_out/ab_w10_gasdark.jsonl 2>/dev/null; cut -c1-330 gpurun_out/ab_w10_gasdark.jsonl
-timeout 50 python tools/ab_probe.py --log2n 24 --kind massive --passes 2 "" "SKIDGPU_TILE_WINDOW=10" > gpurun_out/ab_w10_massive.jsonl 2>/dev/null; cut -c1-330 gpurun_out/ab_w10_massive.jsonl
+timeout 300 python tools/ab_probe.py --log2n 24 --kind gasdark --passes 3 \
+  "" "SKIDGPU_TILE_OVERLAP=1" "" "SKIDGPU_TILE_OVERLAP=1" \
+  > gpurun_out/ab_gasdark.jsonl 2> gpurun_out/ab_gasdark.err; echo "rc=$?"
+timeout 300 python tools/ab_probe.py --log2n 24 --kind massive --passes 2 \
+  "" "SKIDGPU_TILE_OVERLAP=1" "" "SKIDGPU_TILE_OVERLAP=1" \
+  > gpurun_out/ab_massive.jsonl 2> gpurun_out/ab_massive.err; echo "rc=$?"
+cut -c1-330 gpurun_out/ab_gasdark.jsonl; cut -c1-330 gpurun_out/ab_massive.jsonl
+(SKIDGPU_TILE_OVERLAP=1 timeout 400 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/tests_overlap.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests_overlap.log); tail -4 gpurun_out/tests_overlap.log
+(timeout 400 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests.log); tail -4 gpurun_out/tests.log
