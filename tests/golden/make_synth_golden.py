@@ -19,7 +19,10 @@ from oracle import refdump  # noqa: E402
 from skid_b200 import synth, tipsy  # noqa: E402
 
 CASES = {"dark13": ("dark", 1 << 13, 3), "gasdark13": ("gasdark", 1 << 13, 11), "dark14": ("dark", 1 << 14, 5),
-         "massive14": ("massive", 1 << 14, 9)}
+         "massive14": ("massive", 1 << 14, 9),
+         # BASELINE configs[1] semantics: -nsp, exact scatterer handling = the reference with pruning disabled
+         # (skid_ref_dump with SKID_NOPRUNE=1, the one-line patch described in oracle/build_ref.sh)
+         "dark13_nsp": ("dark", 1 << 13, 3)}
 
 
 def main():
@@ -29,7 +32,8 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             f = os.path.join(td, "in.std")
             synth.write_std(snap, f)
-            text, _ = refdump.run_ref(f, snap["ref_args"] + ["-den"], os.path.join(td, "ref"))
+            text, _ = refdump.run_ref(f, snap["ref_args"] + ["-den"], os.path.join(td, "ref"),
+                                      noprune=name.endswith("_nsp"))
             log = refdump.parse_log(text)
             out[name + "_grp"] = tipsy.read_array(os.path.join(td, "ref.grp")).astype(np.int32)
             out[name + "_den"] = tipsy.read_array(os.path.join(td, "ref.den")).astype(np.float32)

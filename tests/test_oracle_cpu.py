@@ -201,7 +201,8 @@ def test_stats_kernel_scheme_model(orc, demo_input, demo_golden):
         assert np.array_equal(ref[f], mod[f]), f
 
 
-SYNTH_CASES = {"dark13": ("dark", 1 << 13, 3), "gasdark13": ("gasdark", 1 << 13, 11), "massive14": ("massive", 1 << 14, 9)}
+SYNTH_CASES = {"dark13": ("dark", 1 << 13, 3), "gasdark13": ("gasdark", 1 << 13, 11), "massive14": ("massive", 1 << 14, 9),
+               "dark13_nsp": ("dark", 1 << 13, 3)}   # -nsp: golden = the reference with pruning disabled (SKID_NOPRUNE)
 
 
 @pytest.mark.parametrize("name", sorted(SYNTH_CASES))
@@ -216,6 +217,8 @@ def test_oracle_pipeline_matches_reference_on_synthetic_boxes(orc, name):
     gold = np.load(os.path.join(GOLDEN, "synth_golden.npz"))
     kind, n, seed = SYNTH_CASES[name]
     snap = synth.make_box(n, seed=seed, kind=kind)
+    if name.endswith("_nsp"):
+        snap["flags"]["bNoPrune"] = True
     res = pipeline.run_port(snap, csmExp2Hub)
     nIttr, nBefore, nUnbound, nGroup, _ = gold[name + "_log"]
     assert abs(res["nIttr"] - nIttr) <= 1
