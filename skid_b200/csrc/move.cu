@@ -1404,6 +1404,10 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.mQueue.alloc(own > 0 ? own : 1);
 		if (move_kernel() == MOVE_TILE) {
 			const size_t nt = ceil_div(own > 0 ? own : 1, TILE);
+			// list offsets are 32-bit: 8.3 M tiles (67 M movers on ONE GPU) would overflow them - fail loudly
+			if (nt * TILE_CAP + (nt / 8 + 1024) * (size_t)BIG_CAP >= (1ull << 32))
+				throw SkidError("skidgpu_move: too many movers on one GPU for the 32-bit tile-list offsets; shard the "
+				                "movers over more GPUs (skidgpu_set_shard)");
 			c.bigBase = (uint32_t)(nt * TILE_CAP);
 			c.nBig = (uint32_t)(nt / 8 + 1024);
 			c.tList.alloc(nt * TILE_CAP + (size_t)c.nBig * BIG_CAP);
