@@ -377,6 +377,22 @@ def main():
     }
     if out["roofline_knn"]["achieved"]:
         out["roofline_knn"]["frac"] = out["roofline_knn"]["achieved"] / peak
+    try:
+        # What actually bounds both kernel families (ncu: DRAM < 2 % of peak, sm__throughput 68-80 %): warp
+        # instruction issue.  Instructions per unit are ncu counts (smsp__inst_executed.sum of the profiles named
+        # below / units of that launch); peak = 148 SMs x 4 schedulers x 1 warp instruction per clock.
+        issue_peak = 148 * 4 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
+        per_gpu_q = n / (world if shard else 1)
+        knn_rate = per_gpu_q * 6800.0 / (st["knn_ms"] / a.steps * 1e-3) if st["knn_ms"] > 0 else None
+        mv_rate = per_gpu_steps * 477.0 / (st["move_kernel_ms"] * 1e-3) if st["move_kernel_ms"] > 0 else None
+        out["issue_roofline"] = {
+            "unit": "warp instructions/s", "peak": issue_peak,
+            "knn": {"inst_per_query": 6800, "achieved": knn_rate, "frac": knn_rate / issue_peak if knn_rate else None,
+                    "source": "profiles/r01_v6_knn_2e22_lines.txt"},
+            "move": {"inst_per_mover_step": 477, "achieved": mv_rate, "frac": mv_rate / issue_peak if mv_rate else None,
+                     "source": "profiles/r01_v6_move_launches_2e24.csv (all kernels of a step)"}}
+    except Exception:
+        pass
     if shard:
         out["config"]["particles_total"] = n
         out["config"]["nccl_bytes_per_step"] = reducer.bytes // max(1, (W + a.steps + 1 + a.steps))
