@@ -1,0 +1,25 @@
+"""CUDA path at BASELINE.json's FULL sizes against golden results of the unmodified reference (CPU hours,
+generated once in the build container: tests/golden/make_full_size_golden.py).  C2 = synthetic dark box 2^21
+with -nsp (reference with pruning disabled); C3 = the bench workload, gas+dark 2^24.  Sorted last on purpose:
+these are the slowest tests (the 2^24 box takes ~40 s to generate on the host)."""
+import numpy as np
+import pytest
+
+import fullsize
+from skid_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_size_box_matches_reference(name):
+    gold = fullsize.load(name)
+    if gold is None:
+        pytest.skip(f"tests/golden/full_{name}.npz not generated")
+    snap = synth.make_box(int(gold["n"]), seed=int(gold["seed"]), kind=str(gold["kind"]))
+    fl = dict(snap["flags"])
+    if name == "C2":
+        fl["bNoPrune"] = True
+    res = api.run_skid(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"], want_arrays=False, **fl)
+    rep = fullsize.compare(gold, res["grp"], res["nIttr"], res["nGroupBefore"], res["nUnbound"], res["nGroup"])
+    print(name, rep)

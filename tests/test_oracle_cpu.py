@@ -227,3 +227,24 @@ def test_oracle_pipeline_matches_reference_on_synthetic_boxes(orc, name):
     assert abs(res["nGroup"] - nGroup) <= 1
     same = np.mean(canonical_labels(gold[name + "_grp"].astype(np.int64)) == canonical_labels(res["grp"]))
     assert same >= 0.999, same
+
+
+def test_fullsize_compare_helper():
+    """tests/fullsize.py (used by the full-size GPU parity test): the sample of canonical group ids reproduces the
+    same-group fraction; renumbering the groups changes nothing; moving 1 % of the particles to another group
+    is detected."""
+    import fullsize
+    g = np.load(os.path.join(GOLDEN, "synth_golden.npz"))
+    grp = g["dark14_grp"].astype(np.int32)
+    nI, nB, nU, nG, _ = [int(v) for v in g["dark14_log"]]
+    sizes = np.sort(np.bincount(grp)[1:])[::-1].astype(np.int32)
+    gold = dict(log=g["dark14_log"], stride=4, sample_canon=fullsize.canonical_min_member(grp)[::4], sizes=sizes)
+    rep = fullsize.compare(gold, grp, nI, nB, nU, nG)
+    assert rep["same_group"] == 1.0
+    perm = np.concatenate([[0], 1 + np.random.default_rng(1).permutation(nG)]).astype(np.int32)
+    assert fullsize.compare(gold, perm[grp], nI, nB, nU, nG)["same_group"] == 1.0     # numbering is irrelevant
+    bad = grp.copy()
+    members = np.nonzero(grp > 0)[0]
+    bad[members[:: max(1, len(members) // (len(grp) // 100))]] = 0                       # ~1 % of all particles
+    with pytest.raises(AssertionError):
+        fullsize.compare(gold, bad, nI, nB, nU, nG)
