@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from skid_b200 import api, synth  # noqa: E402
 
 
-def run(name, pinit, nGas, nDark, nStar, flags, noprune=False, repeat=2):
+def run(name, pinit, nGas, nDark, nStar, flags, noprune=False, repeat=2, golden=None):
     best = None
     for _ in range(repeat):
         res = api.run_skid(pinit, nGas, nDark, nStar, bNoPrune=noprune, want_arrays=False, **flags)
@@ -22,7 +22,17 @@ def run(name, pinit, nGas, nDark, nStar, flags, noprune=False, repeat=2):
             best = (tot, res)
     tot, res = best
     n = len(pinit)
-    print(json.dumps(dict(config=name, n=n, gpu_ms=round(tot, 2), particles_per_s=n / (tot * 1e-3),
+    vs_ref = None
+    if golden is not None:  # full-size golden of the unmodified reference (tests/golden/make_full_size_golden.py)
+        import fullsize
+        gold = fullsize.load(golden)
+        if gold is not None:
+            try:
+                vs_ref = fullsize.compare(gold, res["grp"], res["nIttr"], res["nGroupBefore"], res["nUnbound"], res["nGroup"])
+                vs_ref["reference_cpu_s"] = float(np.sum(gold["times"]))
+            except AssertionError as e:
+                vs_ref = {"MISMATCH": str(e)[:400]}
+    print(json.dumps(dict(config=name, vs_reference_full_size=vs_ref, n=n, gpu_ms=round(tot, 2), particles_per_s=n / (tot * 1e-3),
                           stage_ms={k: round(v, 2) for k, v in res["stage_ms"].items()}, nMove=int(res["nMove"]),
                           nIttr=int(res["nIttr"]), mover_steps=int(res["mover_steps"]),
                           groups_before_unbind=int(res["nGroupBefore"]), unbound=int(res["nUnbound"]),
@@ -34,9 +44,9 @@ def main():
     p, nGas, nDark, nStar, _ = load_demo_input()
     run("C1 dark.std demo (32768 dark)", p, nGas, nDark, nStar, DEMO)
     s = synth.make_box(1 << 21, seed=1234, kind="dark")
-    run("C2 dark 2^21 -nsp", s["pinit"], s["nGas"], s["nDark"], s["nStar"], s["flags"], noprune=True)
+    run("C2 dark 2^21 -nsp", s["pinit"], s["nGas"], s["nDark"], s["nStar"], s["flags"], noprune=True, golden="C2")
     s = synth.make_box(1 << 24, seed=7, kind="gasdark")
-    run("C3 gas+dark 2^24", s["pinit"], s["nGas"], s["nDark"], s["nStar"], s["flags"])
+    run("C3 gas+dark 2^24", s["pinit"], s["nGas"], s["nDark"], s["nStar"], s["flags"], golden="C3")
     s = synth.make_box(1 << 24, seed=1234, kind="massive")
     run("C5 massive halos 2^24, tau x 4", s["pinit"], s["nGas"], s["nDark"], s["nStar"], s["flags"])
 
