@@ -39,6 +39,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particles grouped/sec (density+move+group+unbind)"
 UNIT = "particles/s"
+# the full 2^24 workload through the unmodified reference, measured once in the build container (one core)
+FULL_SIZE_NOTE = ("; the FULL 2^24 box took the reference 2448 s of stage time = 6.85e3 particles/s with identical "
+                  "counters (69 Ittr lines, 138065 groups before unbinding, 55419 groups; profiles/r01_reference_full_size.json)")
 BYTES_PER_MOVER_STEP = 24 * 85 + 24  # SURVEY.md 8d / DESIGN.md: 24 B per containing scatterer (C = 85) + 24 B mover r/w
 
 
@@ -405,7 +408,8 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                                    "sample": f"{what} on a 2^{cpu_log2n}-particle "
                                              f"box of the same generator/flags; sum of its stage timers "
-                                             f"{info['stage_s']:.1f} s (wall {info['wall_s']:.1f} s); host has {os.cpu_count()} cores"}
+                                             f"{info['stage_s']:.1f} s (wall {info['wall_s']:.1f} s); host has {os.cpu_count()} cores"
+                                             + (FULL_SIZE_NOTE if a.kind == "gasdark" and a.log2n == 24 else "")}
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
     if rank == 0:
