@@ -5,6 +5,7 @@
  * word-at-a-time XDR decode (kd.c:141-206).
  *
  *   io_harness fmt <count> <seed>     random + adversarial floats/ints: fmt_g/fmt_int vs snprintf
+ *   io_harness exh <lo> <hi>          EVERY float bit pattern in [lo, hi) (hex): fmt_g vs snprintf for %g and %.10g
  *   io_harness files <n> <seed> <dir> writes .grp/.den/.ray with the fast writers and with fprintf,
  *                                     compares the bytes, prints both timings as one JSON line
  *   io_harness emit <n> <dir>         <dir>/grp.i32, den.f32, ray.f32 (n x 3 displacements) -> <dir>/out.grp,
@@ -408,8 +409,19 @@ static int mode_emit(int n, const char *dir)
 	return rc != 0;
 }
 
+static int mode_exh(const char *slo, const char *shi)
+{
+	const uint64_t lo = strtoull(slo, NULL, 16), hi = strtoull(shi, NULL, 16);
+	uint64_t u;
+	for (u = lo; u < hi; ++u) check_g(bits2f((uint32_t)u));
+	printf("{\"mode\": \"exh\", \"lo\": \"%llx\", \"hi\": \"%llx\", \"checked\": %ld, \"mismatches\": %ld}\n",
+	       (unsigned long long)lo, (unsigned long long)hi, g_checked, g_bad);
+	return g_bad != 0;
+}
+
 int main(int argc, char **argv)
 {
+	if (argc >= 4 && !strcmp(argv[1], "exh")) return mode_exh(argv[2], argv[3]);
 	if (argc >= 4 && !strcmp(argv[1], "emit")) return mode_emit(atoi(argv[2]), argv[3]);
 	if (argc >= 4 && !strcmp(argv[1], "fmt")) return mode_fmt(atol(argv[2]), (uint64_t)atol(argv[3]));
 	if (argc >= 5 && !strcmp(argv[1], "files")) return mode_files(atoi(argv[2]), (uint64_t)atol(argv[3]), argv[4]);
