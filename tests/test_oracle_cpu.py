@@ -248,3 +248,48 @@ def test_fullsize_compare_helper():
     bad[members[:: max(1, len(members) // (len(grp) // 100))]] = 0                       # ~1 % of all particles
     with pytest.raises(AssertionError):
         fullsize.compare(gold, bad, nI, nB, nU, nG)
+
+
+@pytest.mark.parametrize("stars", [False, True])
+def test_stats_match_live_reference_with_species(orc, tmp_path, stars):
+    """orc_stats against the .stat file of the live reference on a gas+dark(+star) box with -gd, Lambda cosmology,
+    z = 0.5 and a temperature cut: gas-mass and star-mass columns, the Hubble term of the velocity dispersion.
+    Inputs of orc_stats are the reference's own .grp / .gtp / .den, so every computed column must print the same."""
+    from oracle import refdump
+    from skid_b200 import synth, tipsy
+    from skid_b200.api import csmExp2Hub
+    if not refdump.have_ref():
+        pytest.skip("oracle/_ref not present")
+    n = 1 << 13
+    snap = synth.make_box(n, seed=11, kind="gasdark")
+    if stars:
+        snap["nStar"] = n // 8
+        snap["nDark"] -= snap["nStar"]
+    f = str(tmp_path / "in.std")
+    synth.write_std(snap, f)
+    refdump.run_ref(f, snap["ref_args"] + ["-den", "-stats"], str(tmp_path / "ref"))
+    ref_lines = open(str(tmp_path / "ref.stat")).read().strip().splitlines()
+    assert len(ref_lines) > 5
+    ref = np.array([[float(t) for t in ln.split()] for ln in ref_lines])
+    grp = tipsy.read_array(str(tmp_path / "ref.grp")).astype(np.int32)
+    den = tipsy.read_array(str(tmp_path / "ref.den")).astype(np.float32)
+    gtp = tipsy.read_gtp(str(tmp_path / "ref.gtp"), standard=True)
+    nGroup = len(ref_lines) + 1
+    rc = np.zeros((nGroup, 3), np.float32)
+    vc = np.zeros((nGroup, 3), np.float32)
+    rb = np.zeros((nGroup, 3), np.float32)
+    rc[1:], vc[1:], rb[1:] = gtp["pos"], gtp["vel"], ref[:, 18:21]
+    p, fl = snap["pinit"], snap["flags"]
+    f32 = lambda v: float(np.float32(v))
+    z = f32(fl["z"])
+    a = f32(1.0 / (1.0 + z))
+    dExpHub = a * csmExp2Hub(a, f32(fl["H0"]), f32(fl["Omega0"]), f32(fl["Lambda"]))
+    rows = orc.stats(p["r"], p["v"], p["fMass"], p["fSoft"], p["fTemp"], den, snap["nGas"], snap["nDark"], grp, nGroup,
+                     rc, vc, (1.0, 1.0, 1.0), 1.0, z, dExpHub, fl["fDensMin"], fl["fTempMax"])
+    lines = orc.stat_lines(rows, rc, vc, rb)
+    assert len(lines) == len(ref_lines)
+    same = sum(x.split()[:18] == y.split()[:18] for x, y in zip(lines, ref_lines))
+    assert same >= len(ref_lines) - 1, [(x, y) for x, y in zip(lines, ref_lines) if x.split()[:18] != y.split()[:18]][:2]
+    assert rows["fGasMass"].sum() > 0
+    if stars:
+        assert rows["fStarMass"].sum() > 0
