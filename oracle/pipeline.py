@@ -33,9 +33,12 @@ def run_port(snap, csm_exp2hub):
     tau = f32(fl["tau"])
     fCvg, fScoop = f32(0.5 * tau), f32(2.0 * tau)          # main.c:343-344
     fStep = f32(0.5 * fCvg)                                # main.c:345
-    nGas = snap["nGas"]
-    if nGas and not fl.get("bGasAndDark", False):
-        raise ValueError("oracle pipeline: gas inputs need -gd (all particles scatter-active)")
+    nGas, nDark, nStar = snap["nGas"], snap["nDark"], snap["nStar"]
+    # the restatement's kNN runs over ALL particles: inputs whose scatter-active set (kd.c:600-627) is everything
+    all_active = (nGas == 0 and nStar == 0) or (nDark == 0 and nStar == 0) or fl.get("bGasAndDark", False)
+    if not all_active:
+        raise ValueError("oracle pipeline: needs an input whose particles are all scatter-active "
+                         "(dark only, gas only, or -gd)")
     times = {}
     # ---- stage 1/2: kNN + density (smDensityInit)
     t0 = time.perf_counter()
@@ -45,11 +48,17 @@ def run_port(snap, csm_exp2hub):
     # ---- stage 3: movers (CutCriterion kd.c:555-597) + flow loop + micro steps
     t0 = time.perf_counter()
     dens_ok = rho >= np.float32(fl["fDensMin"])
-    is_gas = np.arange(n) < nGas
-    movers = np.nonzero(dens_ok & (~is_gas | (p["fTemp"] <= np.float32(fl.get("fTempMax", 3.4e38)))))[0]
+    idx_all = np.arange(n)
+    is_gas, is_star = idx_all < nGas, idx_all >= nGas + nDark
+    is_dark = ~is_gas & ~is_star
+    move = is_gas & dens_ok & (p["fTemp"] <= np.float32(fl.get("fTempMax", 3.4e38)))
+    move |= is_dark & dens_ok                       # dark-only input, or -gd (all_active guarantees one of them)
+    move |= is_star & (not fl.get("bGasOnly", False))  # stars always move unless -go (kd.c:573-593)
+    move &= p["fMass"] <= np.float32(fl.get("fMassMax", 3.4e38))
+    movers = np.nonzero(move)[0]
     idx = np.concatenate([np.arange(n), src])
     epos = np.concatenate([p["r"], rp]).astype(np.float32)
-    bInitial = (nGas == 0 and snap["nStar"] == 0) or fl.get("bForceInitialCut", False)   # main.c:396
+    bInitial = (nGas == 0 and nStar == 0) or fl.get("bForceInitialCut", False)   # main.c:396
     mv = orc.move_loop(epos, ball2[idx], p["fMass"][idx], rho[idx], p["r"][movers], L, (0, 0, 0), fCvg, fStep,
                        bInitial=bInitial, bNoPrune=fl.get("bNoPrune", False))
     times["Moving Particles"] = time.perf_counter() - t0
@@ -70,7 +79,7 @@ def run_port(snap, csm_exp2hub):
     a = f32(1.0 / (1.0 + z))
     fCosmo = f32(a * csm_exp2hub(a, f32(fl["H0"]), f32(fl.get("Omega0", 1.0)), f32(fl.get("Lambda", 0.0))))
     # kd.c:1441: potentials are updated after a removal only for pure-dark or pure-star inputs
-    bSubPot = (nGas == 0 and snap["nStar"] == 0) or (nGas == 0 and snap["nDark"] == 0)
+    bSubPot = (nGas == 0 and nStar == 0) or (nGas == 0 and nDark == 0)
     loose = np.nonzero(grp == 0)[0]
     fScoop2 = np.float32(np.float32(fScoop) ** 2)
     nUnbound = 0

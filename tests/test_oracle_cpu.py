@@ -293,3 +293,25 @@ def test_stats_match_live_reference_with_species(orc, tmp_path, stars):
     assert rows["fGasMass"].sum() > 0
     if stars:
         assert rows["fStarMass"].sum() > 0
+
+
+@pytest.mark.parametrize("name", ["gas_only", "gas_dark_star_gd"])
+def test_oracle_pipeline_species_rules(orc, name):
+    """Species rules of the movers (CutCriterion kd.c:555-597) in the restatement's stage script against goldens of
+    the unmodified reference (tests/golden/species_golden.npz): a gas-only input with a temperature cut, and
+    gas + dark + stars with -gd, where every star moves regardless of its density (223 iterations)."""
+    sys.path.insert(0, GOLDEN)
+    from make_species_golden import make_case
+    from oracle import pipeline
+    from oracle.refdump import canonical_labels
+    from skid_b200.api import csmExp2Hub
+    gold = np.load(os.path.join(GOLDEN, "species_golden.npz"))
+    snap, fl, _ = make_case(name)
+    snap["flags"] = fl
+    res = pipeline.run_port(snap, csmExp2Hub)
+    nIttr, nBefore, nUnbound, nGroup, _, nAct0, _ = [int(v) for v in gold[name + "_log"]]
+    assert res["nMove"] == nAct0
+    assert abs(res["nIttr"] - nIttr) <= 1 and res["nGroupBefore"] == nBefore and abs(res["nGroup"] - nGroup) <= 1
+    assert abs(res["nUnbound"] - nUnbound) <= max(2, nUnbound // 50)
+    same = np.mean(canonical_labels(gold[name + "_grp"].astype(np.int64)) == canonical_labels(res["grp"]))
+    assert same >= 0.999, same
