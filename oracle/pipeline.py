@@ -3,8 +3,8 @@
 
 Used by tests (end-to-end pin of the restatement against the live reference on synthetic boxes) and by
 bench.py as the "port" CPU baseline when the compiled reference (oracle/_ref) did not travel.  Never by
-the product path.  Restrictions of the restatement: all particles scatter-active (dark-only inputs, or
-gas+dark with -gd), cubic period.
+the product path.  Restrictions of the restatement: all particles scatter-active (dark-only or gas-only inputs,
+or any mix with -gd), cubic period.
 """
 import time
 

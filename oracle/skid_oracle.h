@@ -10,7 +10,10 @@
  * Pinning: every function here is checked in tests/test_oracle_cpu.py against
  * tests/golden/demo_golden.npz, which was produced by the UNMODIFIED reference compiled from
  * /root/reference (oracle/build_ref.sh; tests/golden/make_golden.py) - kNN radii bitwise,
- * densities, step-0 gradients and survivors, FoF partition, unbinding counts.
+ * densities, step-0 gradients and survivors, FoF partition, unbinding counts, the .stat file text -
+ * and, as a whole stage script (oracle/pipeline.py), against goldens of the reference on synthetic dark,
+ * gas+dark, gas-only, gas+dark+star, massive-halo and pruning-disabled boxes (tests/golden/synth_golden.npz,
+ * species_golden.npz: same iteration counts, group counts, unbound counts, same-group fraction 1.0).
  */
 #ifndef SKID_ORACLE_H
 #define SKID_ORACLE_H
