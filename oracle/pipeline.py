@@ -3,8 +3,7 @@
 
 Used by tests (end-to-end pin of the restatement against the live reference on synthetic boxes) and by
 bench.py as the "port" CPU baseline when the compiled reference (oracle/_ref) did not travel.  Never by
-the product path.  Restrictions of the restatement: all particles scatter-active (dark-only or gas-only inputs,
-or any mix with -gd), cubic period.
+the product path.  Restriction of the restatement: cubic period.
 """
 import time
 
@@ -34,30 +33,45 @@ def run_port(snap, csm_exp2hub):
     fCvg, fScoop = f32(0.5 * tau), f32(2.0 * tau)          # main.c:343-344
     fStep = f32(0.5 * fCvg)                                # main.c:345
     nGas, nDark, nStar = snap["nGas"], snap["nDark"], snap["nStar"]
-    # the restatement's kNN runs over ALL particles: inputs whose scatter-active set (kd.c:600-627) is everything
-    all_active = (nGas == 0 and nStar == 0) or (nDark == 0 and nStar == 0) or fl.get("bGasAndDark", False)
-    if not all_active:
-        raise ValueError("oracle pipeline: needs an input whose particles are all scatter-active "
-                         "(dark only, gas only, or -gd)")
+    bGD, bGO = fl.get("bGasAndDark", False), fl.get("bGasOnly", False)
+    idx_all = np.arange(n)
+    is_gas, is_star = idx_all < nGas, idx_all >= nGas + nDark
+    is_dark = ~is_gas & ~is_star
+    # ScatterCriterion (kd.c:600-627): which particles carry the density field
+    if nGas == 0 and nStar == 0:
+        active = np.ones(n, bool)                                  # DARK
+    elif nStar == 0:
+        active = np.ones(n, bool) if bGD else is_gas               # GAS, DARK|GAS
+    elif nGas == 0:
+        active = is_star                                           # STAR, DARK|STAR
+    else:
+        active = np.ones(n, bool) if bGD else (is_gas | (is_star & (not bGO)))   # GAS|STAR(|DARK)
+    act = np.nonzero(active)[0]
     times = {}
-    # ---- stage 1/2: kNN + density (smDensityInit)
+    # ---- stage 1/2: kNN + density over the scatter-active particles (smDensityInit)
     t0 = time.perf_counter()
-    ball2, rho = orc.knn_density(p["r"], p["fMass"], fl["nSmooth"], L)
-    src, rp = orc.replicas(p["r"], ball2, L)
+    ball2 = np.zeros(n, np.float32)
+    rho = np.zeros(n, np.float32)
+    ball2[act], rho[act] = orc.knn_density(p["r"][act], p["fMass"][act], fl["nSmooth"], L)
+    src, rp = orc.replicas(p["r"][act], ball2[act], L)
+    src = act[src]
     times["Initial Density"] = time.perf_counter() - t0
     # ---- stage 3: movers (CutCriterion kd.c:555-597) + flow loop + micro steps
     t0 = time.perf_counter()
     dens_ok = rho >= np.float32(fl["fDensMin"])
-    idx_all = np.arange(n)
-    is_gas, is_star = idx_all < nGas, idx_all >= nGas + nDark
-    is_dark = ~is_gas & ~is_star
-    move = is_gas & dens_ok & (p["fTemp"] <= np.float32(fl.get("fTempMax", 3.4e38)))
-    move |= is_dark & dens_ok                       # dark-only input, or -gd (all_active guarantees one of them)
-    move |= is_star & (not fl.get("bGasOnly", False))  # stars always move unless -go (kd.c:573-593)
-    move &= p["fMass"] <= np.float32(fl.get("fMassMax", 3.4e38))
+    gas_rule = is_gas & dens_ok & (p["fTemp"] <= np.float32(fl.get("fTempMax", 3.4e38)))
+    if nGas == 0 and nStar == 0:
+        move = dens_ok
+    elif nStar == 0:
+        move = gas_rule | (is_dark & dens_ok & bGD)
+    elif nGas == 0:
+        move = is_star
+    else:
+        move = gas_rule | (is_dark & dens_ok & bGD) | (is_star & (not bGO))
+    move = move & (p["fMass"] <= np.float32(fl.get("fMassMax", 3.4e38)))
     movers = np.nonzero(move)[0]
-    idx = np.concatenate([np.arange(n), src])
-    epos = np.concatenate([p["r"], rp]).astype(np.float32)
+    idx = np.concatenate([act, src])
+    epos = np.concatenate([p["r"][act], rp]).astype(np.float32)
     bInitial = (nGas == 0 and nStar == 0) or fl.get("bForceInitialCut", False)   # main.c:396
     mv = orc.move_loop(epos, ball2[idx], p["fMass"][idx], rho[idx], p["r"][movers], L, (0, 0, 0), fCvg, fStep,
                        bInitial=bInitial, bNoPrune=fl.get("bNoPrune", False))
