@@ -3,7 +3,7 @@
 
 Used by tests (end-to-end pin of the restatement against the live reference on synthetic boxes) and by
 bench.py as the "port" CPU baseline when the compiled reference (oracle/_ref) did not travel.  Never by
-the product path.  Restriction of the restatement: cubic period.
+the product path.  Restriction of the restatement: the period, if any, is cubic.
 """
 import time
 
@@ -15,6 +15,8 @@ from . import orc
 def _wrap(d, L):
     """min-image of float32 offsets the way the reference does it: > L/2 -> -L, <= -L/2 -> +L (kd.c:1341-1355)."""
     d = d.astype(np.float32)
+    if not L or L <= 0:          # not periodic (fPeriod = FLT_MAX, main.c:125-128): no image is ever closer
+        return d
     h = np.float32(0.5 * L)
     d = np.where(d > h, d - np.float32(L), d).astype(np.float32)
     d = np.where(d <= -h, d + np.float32(L), d).astype(np.float32)
@@ -27,7 +29,7 @@ def run_port(snap, csm_exp2hub):
     p = snap["pinit"]
     fl = snap["flags"]
     n = len(p)
-    L = float(fl["period"])
+    L = float(fl.get("period") or 0.0)      # 0: not periodic
     f32 = lambda v: float(np.float32(v))
     tau = f32(fl["tau"])
     fCvg, fScoop = f32(0.5 * tau), f32(2.0 * tau)          # main.c:343-344
@@ -104,8 +106,9 @@ def run_port(snap, csm_exp2hub):
         rel = p["r"][mem[-1]]
         off = _wrap(final[mm] - rel, L)
         cen = (rel + off.astype(np.float64).mean(axis=0)).astype(np.float32)
-        cen = np.where(cen > 0.5 * L, cen - L, cen)
-        cen = np.where(cen <= -0.5 * L, cen + L, cen).astype(np.float32)
+        if L > 0:
+            cen = np.where(cen > 0.5 * L, cen - L, cen)
+            cen = np.where(cen <= -0.5 * L, cen + L, cen).astype(np.float32)
         dr = _wrap(p["r"][mem] - rel, L)
         dc = _wrap(p["r"][loose] - cen, L)
         sc = loose[(dc ** 2).sum(axis=1) < fScoop2]

@@ -28,6 +28,8 @@ CASES = {
     "gas_dark_star_go": (N // 4, N // 8, ["-go"],        dict(bGasAndDark=False, bGasOnly=True)),  # gas only
     "dark_star":       (0,      N // 4, [],             dict(bGasAndDark=False)),              # stars only
     "gas_only":        (N,      0,      [],             dict(bGasAndDark=False)),              # inType GAS
+    # not a species case but the same kind of golden: the dark box WITHOUT -p (no replicas, no wrapping)
+    "dark_nonperiodic": (0,     0,      [],             dict(bGasAndDark=False, period=None)),
 }
 
 
@@ -42,6 +44,14 @@ def make_case(name):
     fl = dict(snap["flags"])
     fl.update(py)
     args = [a for a in snap["ref_args"] if a != "-gd"] + ref_extra
+    if "period" in py and py["period"] is None:
+        i = args.index("-p")
+        del args[i:i + 2]
+        fl.pop("period")
+        # dark-only input: drop the gas flags of the generator too
+        for k in ("Omega0", "Lambda", "z", "fTempMax"):
+            fl.pop(k, None)
+        args = [a for a in args if a not in ("-O", "0.3", "-Lambda", "0.7", "-z", "0.5", "-t", "30000")]
     return snap, fl, args
 
 

@@ -296,13 +296,14 @@ def test_stats_match_live_reference_with_species(orc, tmp_path, stars):
 
 
 @pytest.mark.parametrize("name", ["gas_only", "gas_dark", "gas_dark_star_go", "gas_dark_star_gd", "gas_dark_star",
-                                  "dark_star"])
+                                  "dark_star", "dark_nonperiodic"])
 def test_oracle_pipeline_species_rules(orc, name):
     """Species rules (ScatterCriterion kd.c:600-627, CutCriterion kd.c:555-597) in the restatement's stage script
     against goldens of the unmodified reference (tests/golden/species_golden.npz) for every input type the
     reference distinguishes: gas only; gas + dark without -gd (only gas scatters and moves); gas + dark + stars
     with -go, with -gd (every star moves regardless of its density, 223 iterations) and plain (gas + stars);
-    dark + stars (stars only).  The goldens come from runs WITHOUT -den: with it the reference scatters from the
+    dark + stars (stars only); plus the dark box without -p (not periodic: no replicas, no wrapping).  The goldens
+    come from runs WITHOUT -den: with it the reference scatters from the
     wrong particles whenever stars are scatter-active (latent bug, kd.c:1541 after kd.c:669-693)."""
     sys.path.insert(0, GOLDEN)
     from make_species_golden import make_case
