@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
+# species rules + non-periodic goldens of the reference (written at the end of round 1, never run on a GPU yet)
+timeout 120 python tools/species_check.py > gpurun_out/species_check.log 2>&1; echo "species rc=$?"; tail -9 gpurun_out/species_check.log
 (timeout 600 python -m pytest tests/test_gpu_stats.py tests/test_gpu_synth_golden.py tests/test_gpu_host_driver.py tests -m gpu -q --durations=20 -p no:cacheprovider > gpurun_out/tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/tests.log)
 tail -8 gpurun_out/tests.log
 timeout 300 python bench.py > gpurun_out/bench_r01_final.json 2> gpurun_out/bench.err; echo "bench rc=$?"
