@@ -4,7 +4,7 @@ the build container, needs oracle/_ref):
 
   C2  synthetic dark box 2^21, seed 1234, demo flags, pruning disabled (= -nsp; skid_ref_dump + SKID_NOPRUNE)
   C3  synthetic gas+dark box 2^24, seed 7 (the bench.py workload), -gd -O 0.3 -Lambda 0.7 -z 0.5 -t 30000
-  C5  synthetic massive-halo box 2^24, seed 7, tau x 4 (optional third argument)
+  C5  synthetic massive-halo box 2^24, seed 7, tau x 4, with -maxgroup 20000 (see EXTRA_ARGS)
 
 Stored per case in tests/golden/full_<name>.npz: the reference's log numbers (Ittr lines, groups before
 unbinding, unbound, groups), its stage times, the sorted group sizes, and for every STRIDE-th particle the
@@ -27,6 +27,10 @@ from skid_b200 import synth, tipsy  # noqa: E402
 
 CASES = {"C2": ("dark", 1 << 21, 1234, True, 4), "C3": ("gasdark", 1 << 24, 7, False, 16),
          "C5": ("massive", 1 << 24, 7, False, 16)}
+# C5: the serial reference needs O(n^2) pair evaluations per group for the potentials - half a day for the 2 M
+# member halo of this box - so its golden is taken with -maxgroup 20000 (groups of >= 20000 members are left
+# untouched by kdUnbind, kd.c:1330): density, move, FoF and the unbinding of all other groups are the full run
+EXTRA_ARGS = {"C5": ["-maxgroup", "20000"]}
 
 
 def canonical_min_member(grp):
@@ -46,7 +50,8 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             f = os.path.join(td, "in.std")
             synth.write_std(snap, f)
-            text, wall = refdump.run_ref(f, snap["ref_args"], os.path.join(td, "ref"), noprune=noprune, timeout=6 * 3600)
+            text, wall = refdump.run_ref(f, snap["ref_args"] + EXTRA_ARGS.get(name, []), os.path.join(td, "ref"),
+                                         noprune=noprune, timeout=6 * 3600)
             log = refdump.parse_log(text)
             grp = tipsy.read_array(os.path.join(td, "ref.grp")).astype(np.int32)
         sizes = np.sort(np.bincount(grp)[1:])[::-1].astype(np.int32)
@@ -57,7 +62,8 @@ def main():
                             ittr=np.array(log["ittr"], np.int32), times=np.array(list(log["times"].values())),
                             time_names=np.array(list(log["times"].keys())), wall_s=wall, sizes=sizes,
                             stride=stride, sample_canon=canon[::stride], n=n, seed=seed, kind=kind,
-                            ref_args=" ".join(snap["ref_args"]) + (" [SKID_NOPRUNE=1]" if noprune else ""))
+                            ref_args=" ".join(snap["ref_args"] + EXTRA_ARGS.get(name, []))
+                            + (" [SKID_NOPRUNE=1]" if noprune else ""))
         print(name, "wall %.0f s" % wall, "log", len(log["ittr"]), log["nGroupBefore"], log["nUnbound"], log["nGroup"],
               flush=True)
 
