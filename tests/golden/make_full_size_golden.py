@@ -26,6 +26,8 @@ from oracle import refdump  # noqa: E402
 from skid_b200 import synth, tipsy  # noqa: E402
 
 CASES = {"C2": ("dark", 1 << 21, 1234, True, 4), "C3": ("gasdark", 1 << 24, 7, False, 16),
+         # the C2 box with the reference's default scatterer pruning (initial cut + ScatterCut: dark-only input)
+         "C2p": ("dark", 1 << 21, 1234, False, 4),
          "C5": ("massive", 1 << 24, 7, False, 16)}
 # C5: the serial reference needs O(n^2) pair evaluations per group for the potentials - half a day for the 2 M
 # member halo of this box - so its golden is taken with -maxgroup 20000 (groups of >= 20000 members are left

@@ -1,6 +1,6 @@
 """CUDA path at BASELINE.json's FULL sizes against golden results of the unmodified reference (CPU hours,
 generated once in the build container: tests/golden/make_full_size_golden.py).  C2 = synthetic dark box 2^21
-with -nsp (reference with pruning disabled); C3 = the bench workload, gas+dark 2^24; C5 = massive halos 2^24 with
+with -nsp (reference with pruning disabled); C2p = the same box with the default scatterer pruning; C3 = the bench workload, gas+dark 2^24; C5 = massive halos 2^24 with
 a 4x linking length and -maxgroup 20000 (the serial reference cannot unbind the 2 M member halo in useful time).  Sorted last on purpose:
 these are the slowest tests (the 2^24 box takes ~40 s to generate on the host)."""
 import numpy as np
@@ -12,7 +12,7 @@ from skid_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["C2", "C3", "C5"])
+@pytest.mark.parametrize("name", ["C2", "C2p", "C3", "C5"])
 def test_full_size_box_matches_reference(name):
     gold = fullsize.load(name)
     if gold is None:
