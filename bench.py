@@ -9,19 +9,23 @@ steps, centres, unbinding, too-small removal) over one synthetic snapshot.  Work
 BASELINE.json configs[2] - synthetic gas+dark box, 2^24 particles, moving both species (-gd),
 Lambda cosmology, unbinding on.  N>1 (torchrun, one rank per GPU), weak
 scaling: ONE snapshot of N x 2^24 particles (N=8: the 2^27 box of configs[3]) sharded as the
-north_star says - particles, trees and scatterers replicated, kNN queries / movers / groups
-sharded, NCCL only for the small agreement points (skid_b200/parallel.py).
-`--mode replicas` instead runs N independent 2^24 snapshots with no collective at all.
+north_star says - particles, tree boxes and scatterers replicated; sorts, kNN queries, movers and
+groups shared between the ranks; the exchanges are issued by the library with NCCL (csrc/dist.cu;
+DESIGN.md 6).  `--mode replicas` instead runs N independent 2^24 snapshots with no collective at all.
 
-value     = particles / device time of the K timed steps with the snapshot already in HBM
-            (CUDA events on the context's stream, max over ranks).
+value     = particles / device time of the K timed steps with the snapshot already in HBM and the results
+            left in HBM (CUDA events on the context's stream, max over ranks).
 e2e       = same metric through the C-ABI with HOST buffers: pinned AoS snapshot -> device inside the
-            timed region, labels + catalogue read back every step.
-roofline  = the dominant kernel (gradient walk + move, k_tile_step, timed together with the tile-list
-            builds and the fallback walk that belong to a step): algorithmic bytes (24*C+24 B
-            per mover-step, C = 85) / device time measured inside this run; one "launch" = one step.
+            timed region, labels + catalogue read back every step (N>1: every rank uploads 1/N of the
+            snapshot, rank 0 reads the results back - what host/skid -gpus N does).
+roofline  = the dominant kernel, k_tile_step (gradient walk + move): algorithmic bytes (SURVEY 8d:
+            24*C+24 B per mover-step, C = 85) / its device time, measured in this run with CUDA events around
+            every launch (skidgpu_set_profile); roofline_builds / roofline_knn: the tile-list builds and the
+            kNN kernel the same way.
+parity    = (N>1) same-group fraction of a 2^20 box run sharded over the N ranks against rank 0 running it
+            alone, measured during warm-up; the run FAILS below 0.999.
 cpu_baseline / --impl reference = the UNMODIFIED reference (oracle/_ref/skid_ref, serial: 1 core) on
-            a bounded sample of the same generator (2^17 particles), timed on this box's host.
+            a bounded sample of the same generator, timed on this box's host.
 """
 import argparse
 import json
@@ -39,10 +43,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particles grouped/sec (density+move+group+unbind)"
 UNIT = "particles/s"
-# the full 2^24 workload through the unmodified reference, measured once in the build container (one core)
-FULL_SIZE_NOTE = ("; the FULL 2^24 box took the reference 2448 s of stage time = 6.85e3 particles/s with identical "
-                  "counters (69 Ittr lines, 138065 groups before unbinding, 55419 groups; profiles/r01_reference_full_size.json)")
 BYTES_PER_MOVER_STEP = 24 * 85 + 24  # SURVEY.md 8d / DESIGN.md: 24 B per containing scatterer (C = 85) + 24 B mover r/w
+KF = {"tile_step": 0, "knn": 1, "builds": 2, "fallback": 3, "prune": 4}   # skidgpu_kernel_ms families
 
 
 def load_peaks():
@@ -51,6 +53,15 @@ def load_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """DRAM bytes per unit of the profiled kernels from this round's ncu --set full captures (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -133,6 +144,30 @@ def cpu_arm(kind, ref_log2n, seed):
     return v, info, "port", log2n
 
 
+def reference_arm(a, workload):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.  The
+    reference is strictly serial, so one core; its cost per particle is flat in N (measured 2^15 .. 2^24), so a
+    bounded sample of the same generator stands for the workload: ONE run of a 2^20 box (the largest that fits the
+    few-minute window; the full 2^24 box takes it ~40 minutes), reused for every warm-up and timed step."""
+    v, info, cpu_kind, cpu_log2n = cpu_arm(a.kind, a.ref_log2n, seed=7)
+    sec = (1 << cpu_log2n) / v
+    sample = (f"ONE run of a 2^{cpu_log2n}-particle box of the same generator/flags, reused for all {a.warmup}+{a.steps} "
+              f"steps (the full 2^{a.log2n} box needs ~{sec * (1 << (a.log2n - cpu_log2n)) / 60:.0f} CPU-minutes at this "
+              f"rate); time = sum of the "
+              + ("reference's own stage timers" if cpu_kind == "reference" else
+                 "stage times of the oracle's C restatement (oracle/pipeline.py; oracle/_ref did not travel)"))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_detail": info,
+    }))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,7 +176,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2n", type=int, default=24, help="particles = 2^log2n (BASELINE metric is quoted at 24)")
     ap.add_argument("--kind", default="gasdark", choices=["dark", "gasdark", "massive"])
-    ap.add_argument("--cpu-log2n", type=int, default=17, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-log2n", type=int, default=17, help="size of the bounded CPU-baseline sample of the default run")
+    ap.add_argument("--ref-log2n", type=int, default=20, help="size of the one sample of --impl reference")
+    ap.add_argument("--parity-log2n", type=int, default=20, help="N>1: size of the sharded-vs-single parity box")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"], help="multi-GPU layout (N>1)")
     a = ap.parse_args()
@@ -154,38 +191,12 @@ def main():
                 f"moving both species, Lambda cosmology, unbinding on (BASELINE configs[2])"
                 if a.kind == "gasdark" else f"synthetic {a.kind} box 2^{a.log2n} particles, periodic L=1")
 
-    # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
-        if rank != 0:
-            return 0
-        W = max(a.warmup, 0)
-        vals = []
-        info = {}
-        cpu_kind, cpu_log2n = "reference", a.cpu_log2n
-        for it in range(W + a.steps):
-            v, info, cpu_kind, cpu_log2n = cpu_arm(a.kind, a.cpu_log2n, seed=7)
-            if it >= W:
-                vals.append((1 << cpu_log2n) / v)
-        sec = float(np.mean(vals))
-        value = (1 << cpu_log2n) / sec
-        sample = (f"2^{cpu_log2n}-particle box of the same generator/flags (full 2^{a.log2n} needs ~{140e-6 * (1 << a.log2n) / 60:.0f} "
-                  f"CPU-minutes); time = sum of the "
-                  + ("reference's own stage timers" if cpu_kind == "reference" else
-                     "stage times of the oracle's C restatement (oracle/pipeline.py; oracle/_ref did not travel)"))
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": cpu_kind, "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "reference_detail": info,
-        }))
-        return 0
+        return reference_arm(a, workload) if rank == 0 else 0
 
     # ------------------------------------------------------------------ B200 arm
     import torch
-    from skid_b200 import api, synth
+    from skid_b200 import api, parallel, synth
     from skid_b200.tipsy import PINIT_DTYPE
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the B200 arm has no CPU fallback", file=sys.stderr)
@@ -200,7 +211,6 @@ def main():
     dev0 = torch.device("cuda", local)
     if shard:
         # one snapshot for everybody: rank 0 generates, NCCL broadcasts the SoA columns
-        from skid_b200 import parallel
         meta = torch.zeros(4, dtype=torch.int64, device=dev0)
         if rank == 0:
             snap = synth.make_box(n, seed=7, kind=a.kind)
@@ -218,7 +228,7 @@ def main():
             dist.broadcast(t, 0)
             dev.append(t)
         fl = synth.make_box(1024, seed=7, kind=a.kind)["flags"]
-        fl["tau"] = float(np.float32(0.0288 * n ** (-1.0 / 3.0)))
+        fl["tau"] = float(np.float32((4.0 if a.kind == "massive" else 1.0) * np.float32(0.0288 * n ** (-1.0 / 3.0))))
         p = np.zeros(n, PINIT_DTYPE)
         for k in range(9):
             h = dev[k].cpu().numpy()
@@ -249,11 +259,11 @@ def main():
 
     per = (fl["period"],) * 3
     sk = api.SkidGPU(per, (0.0, 0.0, 0.0), bPeriodic=True, device=local)
+    sk.set_profile(True)
     reducer = None
     if shard:
-        sk.set_shard(rank, world)
-        reducer = parallel.Reducer(dist, dev0, sk.stream())
-        sk.set_reduce_cb(reducer.cb)
+        parallel.init_comm(sk, dist, rank, world)           # the library's own NCCL communicator
+        reducer = parallel.Reducer(dist, dev0, sk.stream())  # only used by upload_sliced (host -> device slices)
     tau = float(np.float32(fl["tau"]))
     fCvg = float(np.float32(0.5 * tau))
     fScoop = float(np.float32(2.0 * tau))
@@ -264,9 +274,10 @@ def main():
     fCosmo = a32 * api.csmExp2Hub(a32, f32(fl["H0"]), f32(fl.get("Omega0", 1.0)), f32(fl.get("Lambda", 0.0)))
 
     def one_pass(host):
+        fetch = host and rank == 0 if shard else host
         if shard:
             return parallel.run_skid_sharded(sk, reducer, host_aos, snap["nGas"], snap["nDark"], snap["nStar"], fl,
-                                             rank, world, host=host, dev_ptrs=[t.data_ptr() for t in dev])
+                                             rank, world, host=host, dev_ptrs=[t.data_ptr() for t in dev], fetch=fetch)
         sk.log = []
         if host:
             sk.set_particles(host_aos, snap["nGas"], snap["nDark"], snap["nStar"])
@@ -277,31 +288,33 @@ def main():
         sk.kdFoF(tau)
         sk.microstep(5, f32(0.1 * fStep))
         sk.kdCalcCenter(fetch=False)
-        grp, cat, nUnb, nBefore = sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX, fl["nMembers"])
-        return grp, cat, nUnb, nBefore
+        return sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX, fl["nMembers"], fetch=fetch)
 
     stream = torch.cuda.ExternalStream(sk.stream(), device=torch.device("cuda", local))
 
     def timed(host, steps):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        stats = dict(mover_steps=0, move_kernel_ms=0.0, move_launches=0, knn_ms=0.0, stage_ms={}, groups=0)
+        stats = dict(fam_ms={k: 0.0 for k in KF}, fam_n={k: 0 for k in KF}, stage_ms={}, groups=0, d2h=0)
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         l0 = sk.counter(0)
         ms0 = sk.counter(1)
+        cb0 = sk.comm_bytes()
         ev0.record(stream)
         for _ in range(steps):
             grp, cat, nUnb, nBefore = one_pass(host)
-            kms, kl = sk.kernel_ms(0)
-            stats["move_kernel_ms"] += kms
-            stats["move_launches"] += kl
-            stats["knn_ms"] += sk.kernel_ms(1)[0]
+            for k, w in KF.items():
+                ms_, n_ = sk.kernel_ms(w)
+                stats["fam_ms"][k] += ms_
+                stats["fam_n"][k] += n_
             for k, v in sk.stage_ms().items():
                 stats["stage_ms"][k] = stats["stage_ms"].get(k, 0.0) + v / steps
-            stats["groups"] = len(cat) - 1
+            stats["groups"] = sk.nGroup - 1
             stats["groups_before"] = nBefore
             stats["unbound"] = nUnb
+            if grp is not None:
+                stats["d2h"] = grp.nbytes + cat.nbytes
         ev1.record(stream)
         torch.cuda.synchronize()
         if dist is not None:
@@ -310,19 +323,47 @@ def main():
         stats["launches"] = sk.counter(0) - l0
         stats["mover_steps"] = sk.counter(1) - ms0
         stats["nMove"] = sk.nMove
-        stats["d2h"] = grp.nbytes + cat.nbytes
+        cb1 = sk.comm_bytes()
+        stats["comm_bytes"] = (cb1[0] - cb0[0]) / steps
+        stats["comm_calls"] = (cb1[1] - cb0[1]) / steps
         if dist is not None:
-            t = torch.tensor([ms, float(stats["mover_steps"]), stats["move_kernel_ms"]], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
-            tm = t[2:3].clone()
-            dist.all_reduce(t[1:2], op=dist.ReduceOp.SUM)   # mover-steps of all shards
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)        # slowest shard's kernel time
-            ms = float(t[0].item())
-            stats["mover_steps"] = float(t[1].item())
-            stats["move_kernel_ms"] = float(tm.item())
+            t = torch.tensor([ms, float(stats["mover_steps"]), stats["fam_ms"]["tile_step"], stats["fam_ms"]["knn"],
+                              stats["fam_ms"]["builds"], float(stats["d2h"])], device="cuda", dtype=torch.float64)
+            mx = t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)      # slowest rank's times
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms = float(mx[0].item())
+            stats["mover_steps"] = float(t[1].item())      # mover-steps of all shards
+            stats["fam_ms"]["tile_step"], stats["fam_ms"]["knn"], stats["fam_ms"]["builds"] = (float(mx[k].item()) for k in (2, 3, 4))
+            stats["d2h"] = float(mx[5].item())
         return ms, stats
 
     W = max(a.warmup, 3)
+    parity = None
+    if shard:
+        # sharded vs single-GPU on the same small box, once, before the warm-up passes: the driver's evidence that
+        # the N-rank run computes the single-GPU groups
+        from oracle.refdump import canonical_labels
+        ps = synth.make_box(1 << a.parity_log2n, seed=11, kind=a.kind)
+        g_sh, cat_sh, unb_sh, before_sh = parallel.run_skid_sharded(sk, None, ps["pinit"], ps["nGas"], ps["nDark"], ps["nStar"],
+                                                                    ps["flags"], rank, world, host=True, fetch=True)
+        it_sh = len([l for l in sk.log if l[0] == 0])
+        flag = torch.ones(1, device=dev0)
+        if rank == 0:
+            single = api.run_skid(ps["pinit"], ps["nGas"], ps["nDark"], ps["nStar"], device=local, want_arrays=False, **ps["flags"])
+            same = float(np.mean(canonical_labels(single["grp"]) == canonical_labels(g_sh)))
+            parity = {"box": f"{a.kind} 2^{a.parity_log2n}, seed 11", "same_group": same,
+                      "groups": [len(cat_sh) - 1, single["nGroup"]], "groups_before_unbind": [before_sh, single["nGroupBefore"]],
+                      "unbound": [unb_sh, single["nUnbound"]], "ittr": [it_sh, single["nIttr"]]}
+            if same < 0.999 or before_sh != single["nGroupBefore"]:
+                flag[0] = 0
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "sharded run does not reproduce the single-GPU groups", "parity": parity}), flush=True)
+            sk.close()
+            dist.destroy_process_group()
+            return 3
     timed(False, W)                       # warm-up, device-resident inputs
     sampler = ClockSampler(local)
     sampler.start()
@@ -335,71 +376,70 @@ def main():
     value = total_particles * a.steps / (ms_dev * 1e-3)
     e2e_value = total_particles * a.steps / (ms_e2e * 1e-3)
     peak, peak_src = load_peaks()
+    traffic = load_traffic()
     # per GPU: the mover-steps of all shards / N over the slowest shard's kernel time, against ONE GPU's peak
-    per_gpu_steps = st["mover_steps"] / (world if shard else 1)
-    achieved = per_gpu_steps * BYTES_PER_MOVER_STEP / (st["move_kernel_ms"] * 1e-3) / 1e9 if st["move_kernel_ms"] > 0 else 0.0
-    traffic = None
-    try:  # ncu dram__bytes_read+write of the step's kernels per mover-step (profiles/roofline_traffic.json)
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            per = float(json.load(f)["move_dram_bytes_per_mover_step"])
-        traffic = per * per_gpu_steps / max(st["move_launches"], 1)
-    except Exception:
-        pass
+    nshare = world if shard else 1
+    per_gpu_steps = st["mover_steps"] / nshare
+    ts_ms, ts_n = st["fam_ms"]["tile_step"], max(st["fam_n"]["tile_step"], 1)
+    achieved = per_gpu_steps * BYTES_PER_MOVER_STEP / (ts_ms * 1e-3) / 1e9 if ts_ms > 0 else 0.0
+    knn_ms = st["fam_ms"]["knn"] / a.steps
+    qbytes = 16 * fl["nSmooth"] + 24
+    knn_ach = (n / nshare) * qbytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else None
+    bld_ms = st["fam_ms"]["builds"]
+
+    def per_launch(key, units):
+        v = traffic.get(key)
+        return None if v is None else float(v) * units
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "particles_per_gpu": 1 << a.log2n, "nSmooth": fl["nSmooth"], "tau": tau,
                    "parallelism": "1 GPU" if world == 1 else (
-                       f"one {n}-particle snapshot sharded over {world} GPUs: replicated scatterers/trees, sharded "
-                       f"kNN queries, movers and groups; NCCL all-reduce at {reducer.calls // max(1, (W + a.steps + 1 + a.steps))} agreement "
-                       f"points per step" if shard else f"{world} independent snapshots, one per GPU"),
+                       f"one {n}-particle snapshot sharded over {world} GPUs: replicated particles/boxes/scatterers; "
+                       f"sorts, kNN queries, movers and groups shared; {st['comm_calls']:.0f} NCCL exchanges per step issued "
+                       f"by the library" if shard else f"{world} independent snapshots, one per GPU"),
                    "l2": "inputs (604 MB SoA at 2^24) larger than the 126 MB L2; no explicit flush",
                    "movers": st["nMove"], "groups_before_unbind": st["groups_before"], "groups": st["groups"],
                    "unbound": st["unbound"]},
         "stage_ms": st["stage_ms"],
-        "knn_queries_per_s": n / (st["knn_ms"] / a.steps * 1e-3) if st["knn_ms"] > 0 else None,
+        "knn_queries_per_s": (n / nshare) * nshare / (knn_ms * 1e-3) if knn_ms > 0 else None,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_aos.nbytes),
                 "d2h_bytes_per_step": int(st_e["d2h"]), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["launches"]),
         "clocks": clocks,
-        "roofline": {"kernel": "k_tile_step (+ k_super_walk/k_tile_filter list builds and the k_move_step fallback: everything a step launches)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "roofline": {"kernel": "k_tile_step (gradient walk + move; one launch per step, timed alone)", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": per_launch("tile_step_dram_bytes_per_mover_step", per_gpu_steps / ts_n),
+                     "traffic_source": traffic.get("source"),
                      "peak_source": peak_src, "bytes_per_mover_step": BYTES_PER_MOVER_STEP,
                      "mover_steps_per_step": st["mover_steps"] / a.steps,
-                     "launches_per_step": st["move_launches"] / a.steps,
-                     "avg_launch_ms": st["move_kernel_ms"] / max(st["move_launches"], 1),
-                     "share_of_step": st["move_kernel_ms"] / ms_dev},
+                     "launches_per_step": st["fam_n"]["tile_step"] / a.steps,
+                     "avg_launch_ms": ts_ms / ts_n, "share_of_step": ts_ms / ms_dev},
+        # the tile-list builds of the same stage (re-sort, k_super_walk, k_tile_filter, k_tile_walk), one span per rebuild:
+        # algorithmic bytes = one more pass over the same scatterer records per mover and rebuild
+        "roofline_builds": {"kernel": "k_super_walk + k_tile_filter + k_tile_walk (+ re-sort every 4th rebuild)", "bound": "hbm",
+                            "unit": "GB/s", "peak": peak, "ms_per_step": bld_ms / a.steps,
+                            "rebuilds_per_step": st["fam_n"]["builds"] / a.steps, "share_of_step": bld_ms / ms_dev,
+                            "achieved": (per_gpu_steps / 5.0) * BYTES_PER_MOVER_STEP / (bld_ms * 1e-3) / 1e9 if bld_ms > 0 else None,
+                            "note": "units = movers present at a rebuild (mover-steps / 5)"},
+        "fallback_ms_per_step": st["fam_ms"]["fallback"] / a.steps, "prune_ms_per_step": st["fam_ms"]["prune"] / a.steps,
         # second kernel family, for the north_star's "kNN walk vs HBM roofline" line (16k+24 B per query)
-        "roofline_knn": {"kernel": "k_knn_density", "bound": "hbm", "unit": "GB/s", "peak": peak,
-                         "bytes_per_query": 16 * fl["nSmooth"] + 24,
-                         "achieved": (n / (world if shard else 1)) * (16 * fl["nSmooth"] + 24) / (st["knn_ms"] / a.steps * 1e-3) / 1e9
-                         if st["knn_ms"] > 0 else None,
-                         "note": "on-chip bound by design: neighbouring queries share their neighbours through L1/L2 "
-                                 "(ncu: 33 B of DRAM traffic per query, issue-active 77 %)"},
+        "roofline_knn": {"kernel": "k_knn_density", "bound": "hbm", "unit": "GB/s", "peak": peak, "bytes_per_query": qbytes,
+                         "achieved": knn_ach, "frac": knn_ach / peak if knn_ach else None, "ms": knn_ms,
+                         "traffic": per_launch("knn_dram_bytes_per_query", n / nshare),
+                         "l2": traffic.get("knn_l2"),
+                         "note": "on-chip bound by design: neighbouring queries share their neighbours through L1/L2, so DRAM "
+                                 "traffic is a few per cent of the algorithmic bytes; `l2` holds the ncu L2 figures of this "
+                                 "round's capture (profiles/)"},
     }
-    if out["roofline_knn"]["achieved"]:
-        out["roofline_knn"]["frac"] = out["roofline_knn"]["achieved"] / peak
-    try:
-        # What actually bounds both kernel families (ncu: DRAM < 2 % of peak, sm__throughput 68-80 %): warp
-        # instruction issue.  Instructions per unit are ncu counts (smsp__inst_executed.sum of the profiles named
-        # below / units of that launch); peak = 148 SMs x 4 schedulers x 1 warp instruction per clock.
-        issue_peak = 148 * 4 * float(clocks.get("sm_mhz") or 1965.0) * 1e6
-        per_gpu_q = n / (world if shard else 1)
-        knn_rate = per_gpu_q * 6800.0 / (st["knn_ms"] / a.steps * 1e-3) if st["knn_ms"] > 0 else None
-        mv_rate = per_gpu_steps * 477.0 / (st["move_kernel_ms"] * 1e-3) if st["move_kernel_ms"] > 0 else None
-        out["issue_roofline"] = {
-            "unit": "warp instructions/s", "peak": issue_peak,
-            "knn": {"inst_per_query": 6800, "achieved": knn_rate, "frac": knn_rate / issue_peak if knn_rate else None,
-                    "source": "profiles/r01_v6_knn_2e22_lines.txt"},
-            "move": {"inst_per_mover_step": 477, "achieved": mv_rate, "frac": mv_rate / issue_peak if mv_rate else None,
-                     "source": "profiles/r01_v6_move_launches_2e24.csv (all kernels of a step)"}}
-    except Exception:
-        pass
+    if out["roofline_builds"]["achieved"]:
+        out["roofline_builds"]["frac"] = out["roofline_builds"]["achieved"] / peak
     if shard:
         out["config"]["particles_total"] = n
-        out["config"]["nccl_bytes_per_step"] = reducer.bytes // max(1, (W + a.steps + 1 + a.steps))
-        out["config"]["reduce_callback_host_ms_per_step"] = 1e3 * reducer.host_s / max(1, (W + a.steps + 1 + a.steps))
+        out["config"]["nccl_bytes_per_step"] = st["comm_bytes"]
+        out["parity"] = parity
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             v, info, cpu_kind, cpu_log2n = cpu_arm(a.kind, a.cpu_log2n, seed=7)
@@ -408,8 +448,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": cpu_kind,
                                    "sample": f"{what} on a 2^{cpu_log2n}-particle "
                                              f"box of the same generator/flags; sum of its stage timers "
-                                             f"{info['stage_s']:.1f} s (wall {info['wall_s']:.1f} s); host has {os.cpu_count()} cores"
-                                             + (FULL_SIZE_NOTE if a.kind == "gasdark" and a.log2n == 24 else "")}
+                                             f"{info['stage_s']:.1f} s (wall {info['wall_s']:.1f} s); host has {os.cpu_count()} cores"}
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"unavailable: {e}"}
     if rank == 0:

@@ -4,6 +4,10 @@
  * include/skidgpu.h.  Flags are the reference's (main.c:140-335) plus two extensions:
  *   -nsp       never prune scatterers (README:29-32 describes it; main.c never implemented it)
  *   -gpu <n>   CUDA device ordinal (default 0)
+ *   -gpus <N>  share the run between N GPUs (devices n .. n+N-1) of this node: one context and one host thread per
+ *              GPU, every context gets the snapshot and makes the same stage calls, the library exchanges what the
+ *              ranks must agree on with NCCL over NVLink (include/skidgpu.h: skidgpu_comm_init); rank 0 writes the
+ *              outputs.  Results are those of one GPU.
  */
 #include <float.h>
 #include <limits.h>
@@ -39,7 +43,7 @@ static void usage(void)
 	      "     [-c <xyzCenter>]\n"
 	      "     [-cx <xCenter>] [-cy <yCenter>] [-cz <zCenter>]\n"
 	      "OUTPUT arguments:\n"
-	      "     [-o <Output Name>] [-ray] [-den] [-stats] [-diag] [-gpu <device>]\n"
+	      "     [-o <Output Name>] [-ray] [-den] [-stats] [-diag] [-gpu <device>] [-gpus <nGpu>]\n"
 	      "\nSee man page skid(1).\n",
 	      stderr);
 	exit(1);
@@ -50,7 +54,7 @@ typedef struct {
 	int bTau, bCvg, bScoop, bEps, bPeriodic, bStandard;
 	int nSmooth, nMembers, nMaxMembers, iSoftType;
 	int bNoUnbind, bGasAndDark, bGasOnly, bUnbindOnly, bForceInitialCut, bNoPrune;
-	int bOutRay, bOutDens, bOutStats, bOutDiag, iDevice;
+	int bOutRay, bOutDens, bOutStats, bOutDiag, iDevice, nGpus;
 	float fTau, z, Omega0, Lambda, fQuintess, G, H0;
 	float fDensMin, fTempMax, fMassMax, fCvg, fScoop, fEps;
 	float fPeriod[3], fCenter[3];
@@ -102,6 +106,7 @@ static const optdef g_opts[] = {
     {"-diag", A_FLAG, OFF(bOutDiag), 0, 1},
     {"-std", A_FLAG, OFF(bStandard), 0, 1},
     {"-gpu", A_INT, OFF(iDevice), 0, 0},
+    {"-gpus", A_INT, OFF(nGpus), 0, 0},
 };
 
 static void parse_args(int argc, char **argv, options *o)
@@ -118,6 +123,7 @@ static void parse_args(int argc, char **argv, options *o)
 	o->nMembers = 8;
 	o->nMaxMembers = INT_MAX;
 	o->iSoftType = SKIDGPU_SPLINE;
+	o->nGpus = 1;
 	for (j = 0; j < 3; ++j) o->fPeriod[j] = FLT_MAX;
 	strcpy(o->achName, "skid");
 	while (i < argc) {
@@ -156,6 +162,7 @@ static void parse_args(int argc, char **argv, options *o)
 		if (!matched) usage();
 	}
 	if (!o->bTau) usage(); /* main.c:339 */
+	if (o->nGpus < 1) usage();
 	if (!o->bCvg) o->fCvg = 0.5 * o->fTau;
 	if (!o->bScoop) o->fScoop = 2.0 * o->fTau;
 }
@@ -276,6 +283,73 @@ static int job_create(void *p)
 	return rc;
 }
 
+/* -gpus N: ranks 1 .. N-1.  Each runs the stage script of main() on its own context and device from its own host
+ * thread, with no outputs (rank 0 = the main thread owns those); the library keeps the ranks in step. */
+typedef struct {
+	pthread_t th;
+	const options *o;
+	const snapshot *s;
+	int rank;
+	unsigned char id[SKIDGPU_UNIQUE_ID_BYTES];
+	const int *piGroup; /* -unbind restart: the catalogue read by the main thread */
+	int nGroup;
+	const skidgpu_pgroup *centres;
+	float fStep;
+	double fCosmo;
+} gpu_worker;
+
+static void *worker_main(void *p)
+{
+	gpu_worker *w = (gpu_worker *)p;
+	const options *o = w->o;
+	skidgpu_ctx *ctx = NULL;
+	int nx = 0, nMove = 0, nIttr = 0, nGroup = 1, nUnbound = 0, nBefore = 0;
+	if (skidgpu_create(&ctx, o->iDevice + w->rank, o->fPeriod, o->fCenter, o->bPeriodic, 0)) die(NULL, "skidgpu_create (worker)");
+	if (skidgpu_comm_init(ctx, w->id, w->rank, o->nGpus)) die(ctx, "skidgpu_comm_init (worker)");
+	if (skidgpu_set_particles(ctx, w->s->p, w->s->n, w->s->nGas, w->s->nDark, w->s->nStar)) die(ctx, "skidgpu_set_particles (worker)");
+	if (o->bUnbindOnly) {
+		if (skidgpu_set_groups(ctx, w->piGroup, w->nGroup, w->centres)) die(ctx, "skidgpu_set_groups (worker)");
+	} else {
+		if (skidgpu_density(ctx, o->nSmooth, o->bGasAndDark, o->bGasOnly, NULL, NULL, &nx)) die(ctx, "skidgpu_density (worker)");
+		if (skidgpu_move(ctx, o->fDensMin, o->fTempMax, o->fMassMax, o->fCvg, w->fStep, o->bForceInitialCut, o->bNoPrune, NULL,
+		                 NULL, &nMove, &nIttr))
+			die(ctx, "skidgpu_move (worker)");
+		if (skidgpu_fof(ctx, o->fTau, &nGroup)) die(ctx, "skidgpu_fof (worker)");
+		if (skidgpu_microstep(ctx, PRUNE_STEPS, MICRO_STEP * w->fStep, NULL, NULL)) die(ctx, "skidgpu_microstep (worker)");
+		if (skidgpu_centers(ctx, NULL, NULL)) die(ctx, "skidgpu_centers (worker)");
+	}
+	if (o->bEps && skidgpu_set_soft(ctx, o->fEps)) die(ctx, "skidgpu_set_soft (worker)");
+	if (skidgpu_unbind(ctx, o->G, o->z, w->fCosmo, o->iSoftType, o->fScoop, o->bNoUnbind, o->nMaxMembers, o->nMembers, NULL, NULL,
+	                   &nGroup, &nUnbound, &nBefore))
+		die(ctx, "skidgpu_unbind (worker)");
+	skidgpu_destroy(ctx);
+	return NULL;
+}
+
+static void start_workers(gpu_worker *w, const options *o, const snapshot *s, const int *piGroup, int nGroup,
+                          const skidgpu_pgroup *centres, float fStep)
+{
+	int r;
+	const float fShift = 1.0 / (1.0 + o->z);
+	const double fCosmo = fShift * cosmo_exp2hub(fShift, o->H0, o->Omega0, o->Lambda, 0.0, o->fQuintess);
+	if (skidgpu_comm_unique_id(w[0].id)) die(NULL, "skidgpu_comm_unique_id");
+	for (r = 0; r < o->nGpus; ++r) {
+		w[r].o = o;
+		w[r].s = s;
+		w[r].rank = r;
+		if (r) memcpy(w[r].id, w[0].id, sizeof w[0].id);
+		w[r].piGroup = piGroup;
+		w[r].nGroup = nGroup;
+		w[r].centres = centres;
+		w[r].fStep = fStep;
+		w[r].fCosmo = fCosmo;
+		if (r && pthread_create(&w[r].th, NULL, worker_main, &w[r])) {
+			fprintf(stderr, "ERROR: could not start the host thread of GPU %d\n", r);
+			exit(1);
+		}
+	}
+}
+
 int main(int argc, char **argv)
 {
 	options o;
@@ -293,6 +367,8 @@ int main(int argc, char **argv)
 	int *mvOrder = NULL;
 	float *mvR = NULL;
 	double t0 = wall(), tRead, tInit, tStages, tEnd; /* host wall clock, reported with SKID_HOST_TIMING=1 */
+	gpu_worker *workers = NULL;
+	int gtpRc = 0;
 
 	g_lap.last = t0;
 	printf("SKID v1.4.1 (B200 GPU hot path): group finder compatible with SKID v1.4.1, Stadel 2000\n");
@@ -314,25 +390,32 @@ int main(int argc, char **argv)
 
 	if (bg_wait(&createJob)) die(NULL, "skidgpu_create");
 	lap("wait_context");
-	if (skidgpu_set_particles(ctx, s.p, s.n, s.nGas, s.nDark, s.nStar)) die(ctx, "skidgpu_set_particles");
 	piGroup = (int *)calloc((size_t)s.n, sizeof(int));
 	rho = (float *)calloc((size_t)s.n, sizeof(float));
-	tInit = wall();
-	lap("upload");
-
 	if (o.bUnbindOnly) {
 		/* main.c:349-373: strip a trailing .grp, read <name>.grp and, if present, <name>.gtp */
 		size_t len = strlen(o.achGroup);
-		int rc;
 		if (len >= 4 && !strcmp(o.achGroup + len - 4, ".grp")) o.achGroup[len - 4] = 0;
 		snprintf(achFile, sizeof achFile, "%s.grp", o.achGroup);
 		nGroup = grp_read(achFile, s.n, piGroup);
 		if (nGroup < 0) return 1;
 		cat = (skidgpu_pgroup *)calloc((size_t)nGroup + 1, sizeof(skidgpu_pgroup));
 		snprintf(achFile, sizeof achFile, "%s.gtp", o.achGroup);
-		rc = gtp_read(achFile, o.bStandard, nGroup, cat);
-		if (rc < 0) return 1;
-		if (skidgpu_set_groups(ctx, piGroup, nGroup, rc ? cat : NULL)) die(ctx, "skidgpu_set_groups");
+		gtpRc = gtp_read(achFile, o.bStandard, nGroup, cat);
+		if (gtpRc < 0) return 1;
+	}
+	if (o.nGpus > 1) { /* the other GPUs: one host thread each; this thread is rank 0 */
+		workers = (gpu_worker *)calloc((size_t)o.nGpus, sizeof(gpu_worker));
+		start_workers(workers, &o, &s, piGroup, nGroup, gtpRc ? cat : NULL, fStep);
+		if (skidgpu_comm_init(ctx, workers[0].id, 0, o.nGpus)) die(ctx, "skidgpu_comm_init");
+		lap("comm_init");
+	}
+	if (skidgpu_set_particles(ctx, s.p, s.n, s.nGas, s.nDark, s.nStar)) die(ctx, "skidgpu_set_particles");
+	tInit = wall();
+	lap("upload");
+
+	if (o.bUnbindOnly) {
+		if (skidgpu_set_groups(ctx, piGroup, nGroup, gtpRc ? cat : NULL)) die(ctx, "skidgpu_set_groups");
 	} else {
 		if (skidgpu_density(ctx, o.nSmooth, o.bGasAndDark, o.bGasOnly, rho, NULL, &nExtra)) die(ctx, "skidgpu_density");
 		lap("density");
@@ -420,6 +503,11 @@ int main(int argc, char **argv)
 		        "{\"host_wall_s\": {\"read\": %.3f, \"create_upload\": %.3f, \"stages_with_overlapped_writers\": %.3f, "
 		        "\"final_writers\": %.3f, \"total\": %.3f}, \"n\": %d, \"threads\": %d}\n",
 		        tRead - t0, tInit - tRead, tStages - tInit, tEnd - tStages, tEnd - t0, s.n, host_threads());
+	}
+	if (workers) {
+		int r;
+		for (r = 1; r < o.nGpus; ++r) pthread_join(workers[r].th, NULL);
+		free(workers);
 	}
 	skidgpu_destroy(ctx);
 	free(mvOrder);

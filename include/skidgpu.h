@@ -75,8 +75,23 @@ const char *skidgpu_last_error(skidgpu_ctx *ctx);
  * pool growth on its critical path.  Clamped to half of the free device memory; never changes results. */
 int skidgpu_reserve(skidgpu_ctx *ctx, unsigned long long bytes);
 
-/* Multi-GPU sharding: this context owns movers/groups shard `rank` of `nranks`.
- * Default 0 of 1.  Scatterers and trees are always replicated. */
+/* Multi-GPU (no reference equivalent - the reference is serial).  One context per GPU, each driven
+ * by its own host thread (host/skid -gpus N) or its own process (bench.py under torchrun); EVERY context gets
+ * the same snapshot (skidgpu_set_particles) and makes the same stage calls.  Particles, trees and scatterers
+ * are replicated; the sorts behind the tree builds, the kNN queries, the movers and the groups to unbind are
+ * shared between the ranks.  The library issues the few exchanges itself with NCCL over NVLink, on the context's
+ * stream: all-gather of fBall2 and all-reduce of the f64 density partials, max of the step-0 "touched" flags,
+ * min of fScatDens every step, sum of the active-mover / scatterer counts every 5 steps, all-gather of the
+ * converged mover positions before grouping, min of labels + sum of the changed catalogue rows after unbinding.
+ *   skidgpu_comm_unique_id   rank 0 makes the 128-byte NCCL id and hands it to the others (any transport)
+ *   skidgpu_comm_init        collective over all nranks contexts (ncclCommInitRank); implies skidgpu_set_shard
+ *   skidgpu_comm_bytes       payload bytes / number of collectives issued by this context since create
+ * NCCL (libnccl.so.2) is loaded at the first of these calls; a single-GPU run never needs it. */
+#define SKIDGPU_UNIQUE_ID_BYTES 128
+int skidgpu_comm_unique_id(void *id128);
+int skidgpu_comm_init(skidgpu_ctx *ctx, const void *id128, int rank, int nranks);
+long long skidgpu_comm_bytes(skidgpu_ctx *ctx, long long *nCalls);
+/* rank/nranks without a communicator: exchanges then go through the callback below (test shim). */
 int skidgpu_set_shard(skidgpu_ctx *ctx, int rank, int nranks);
 
 /* What kdReadTipsy (kd.c:122-222, main.c:348) leaves in kd->pInit: n = nGas+nDark+nStar
@@ -94,25 +109,13 @@ int skidgpu_set_particles_dev(skidgpu_ctx *ctx, const float *dx, const float *dy
 /* kdSetSoft (kd.c:103-110, main.c:464): override every softening. */
 int skidgpu_set_soft(skidgpu_ctx *ctx, float fEps);
 
-/* Multi-GPU exchange hook.  When nranks > 1 the library calls `cb` at the few points where ranks
- * must agree: the buffer is DEVICE memory of this context, the call is made after all
- * producing work has been enqueued on the context's stream (skidgpu_stream) and the reduced result
- * must be visible to work enqueued on that stream afterwards (e.g. an NCCL all-reduce issued on it).
- * dtype: 0 int32, 1 uint8, 2 float32, 3 float64.  op: 0 min, 1 max, 2 sum.  Return 0 on success.
- * Call sites: sum of fBall2/density partials (sharded kNN queries), max of the step-0 "touched"
- * flags, min of fScatDens every step, sum of the active-mover count every 5 steps, min of labels and
- * sum of catalogue rows / unbound count after the sharded unbinding. */
+/* Test shim for the exchanges above when no communicator is set (skidgpu_set_shard only): the library calls
+ * `cb` instead of NCCL.  The buffer is DEVICE memory of this context, the call is made after all producing work
+ * has been enqueued on the context's stream (skidgpu_stream) and the reduced result must be visible to work
+ * enqueued on that stream afterwards.  dtype: 0 int32, 1 uint8, 2 float32, 3 float64.  op: 0 min, 1 max, 2 sum.
+ * All-gathers are expressed as zero-fill + sum.  Return 0 on success. */
 typedef int (*skidgpu_reduce_cb)(void *user, void *dev, long long count, int dtype, int op);
 int skidgpu_set_reduce_cb(skidgpu_ctx *ctx, skidgpu_reduce_cb cb, void *user);
-
-/* Device arrays x,y,z (nMove floats each) of the current mover positions.  Movers are owned
- * block-cyclically (blocks of 256 consecutive movers of the Morton-ordered list, block j -> rank
- * j % nranks; [lo,hi) is only meaningful for the contiguous layout of SKIDGPU_MOVE_KERNEL=list).
- * Before skidgpu_fof and skidgpu_centers the caller exchanges positions: skidgpu_mask_unowned_movers
- * zeroes the entries other ranks own, then one all-reduce(sum) per array makes every rank hold
- * every mover (positions of movers owned by other ranks are stale otherwise). */
-int skidgpu_mover_arrays(skidgpu_ctx *ctx, float **dx, float **dy, float **dz, int *nMove, int *lo, int *hi);
-int skidgpu_mask_unowned_movers(skidgpu_ctx *ctx);
 
 /* kdScatterActive + kdBuildTree + smInit + smDensityInit (main.c:374-378):
  * tree over the scatter-active species, exact periodic k-nearest (k = nSmooth, self
@@ -134,7 +137,9 @@ int skidgpu_get_neighbors(skidgpu_ctx *ctx, int *nbr, float *d2);
  * kd.c:555-597), then step 0 with the initial scatterer cut (bInitial = dark-only input
  * || bForceInitialCut), then blocks of 5 steps + kdPruneInactive until no mover is active.
  * bNoPrune = the "-nsp" extension: never remove scatterers.
- * Outputs: *nMove movers, *nIttr = number of "Ittr" lines printed (blocks + 1). */
+ * Outputs: *nMove movers, *nIttr = number of "Ittr" lines printed (blocks + 1).
+ * The loop is driven from the device: the active count stays in device memory, the host enqueues blocks a few
+ * ahead of the counts it has read back, so `cb` is called a block or two after the block it reports (in order). */
 int skidgpu_move(skidgpu_ctx *ctx, float fDensMin, float fTempMax, float fMassMax,
                  float fCvg, float fStep, int bForceInitialCut, int bNoPrune,
                  skidgpu_log_cb cb, void *user, int *nMove, int *nIttr);
@@ -153,11 +158,6 @@ int skidgpu_microstep(skidgpu_ctx *ctx, int nSteps, float fStep, skidgpu_log_cb 
 
 /* Moved positions for kdOutVector (kd.c:1550-1608): iOrder[nMove] ascending, r3[3*nMove]. */
 int skidgpu_get_moved(skidgpu_ctx *ctx, int *iOrder, float *r3);
-
-/* Multi-GPU exchange of converged mover positions before FoF: device pointers
- * to this context's full mover position array (x,y,z each nMove floats, contiguous in
- * that order) and the [lo,hi) mover range this shard owns. */
-int skidgpu_moved_dev(skidgpu_ctx *ctx, float **dxyz, int *nMove, int *lo, int *hi);
 
 /* kdInitpGroup + kdCalcCenter (main.c:452-453).  piGroup_by_iOrder: n ints (NULL ok).
  * g: nGroup entries (entry 0 = the non-group; NULL ok). */
@@ -206,10 +206,17 @@ double skidgpu_stage_ms(skidgpu_ctx *ctx, int stage);
  * active movers), entity-hit interactions are not counted on the device. */
 long long skidgpu_counter(skidgpu_ctx *ctx, int which); /* 0 launches, 1 mover-steps, 2 kNN queries, 3 unbind pair evaluations */
 
-/* Device time (ms, CUDA events on the context's stream) spent in the dominant kernels during the
- * last call of their stage: which 0 = gradient-walk/move kernel launches of skidgpu_move (sum),
- * 1 = the kNN+density kernel of skidgpu_density; *nLaunches (nullable) = launches covered. */
+/* Device time (ms, CUDA events on the context's stream, recorded without synchronising the host) spent in
+ * each kernel family during the last call of its stage; recorded only after skidgpu_set_profile(ctx, 1).
+ * which: 0 = k_tile_step (gradient walk + move, one launch per step), 1 = k_knn_density, 2 = tile-list builds
+ * (re-sort, k_super_walk, k_tile_filter, k_tile_walk), 3 = per-step fallbacks (short-tile walks, own-walk movers),
+ * 4 = prune + counts.  *nLaunches (nullable) = number of spans covered. */
 double skidgpu_kernel_ms(skidgpu_ctx *ctx, int which, int *nLaunches);
+int skidgpu_set_profile(skidgpu_ctx *ctx, int bOn);
+
+/* Test hook: 0 = tile kernels (default), 1 = the v1 kernel (a tree walk per mover and step) for regression
+ * comparisons.  Set before skidgpu_move. */
+int skidgpu_debug_move_kernel(skidgpu_ctx *ctx, int which);
 
 /* The CUDA stream (cudaStream_t) all work of this context is issued on, for callers that want to
  * bracket calls with their own events. */

@@ -35,10 +35,12 @@ EXPORTS = [
     "skidgpu_create", "skidgpu_destroy", "skidgpu_last_error", "skidgpu_reserve", "skidgpu_set_shard", "skidgpu_set_particles",
     "skidgpu_set_particles_dev", "skidgpu_set_soft", "skidgpu_density", "skidgpu_keep_neighbors",
     "skidgpu_get_neighbors", "skidgpu_move", "skidgpu_keep_step0", "skidgpu_get_step0", "skidgpu_fof",
-    "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_moved_dev", "skidgpu_centers", "skidgpu_set_groups",
+    "skidgpu_microstep", "skidgpu_get_moved", "skidgpu_centers", "skidgpu_set_groups",
     "skidgpu_unbind", "skidgpu_stats", "skidgpu_stage_ms", "skidgpu_counter", "skidgpu_debug_sort", "skidgpu_debug_scan",
-    "skidgpu_kernel_ms", "skidgpu_stream", "skidgpu_set_reduce_cb", "skidgpu_mover_arrays", "skidgpu_mask_unowned_movers",
+    "skidgpu_kernel_ms", "skidgpu_stream", "skidgpu_set_reduce_cb", "skidgpu_comm_unique_id", "skidgpu_comm_init",
+    "skidgpu_comm_bytes", "skidgpu_set_profile", "skidgpu_debug_move_kernel",
 ]
+UNIQUE_ID_BYTES = 128
 
 
 def load_library():
@@ -70,7 +72,6 @@ def load_library():
     lib.skidgpu_fof.argtypes = [vp, f, P(i)]
     lib.skidgpu_microstep.argtypes = [vp, i, f, LOG_CB, vp]
     lib.skidgpu_get_moved.argtypes = [vp, vp, vp]
-    lib.skidgpu_moved_dev.argtypes = [vp, P(vp), P(i), P(i), P(i)]
     lib.skidgpu_centers.argtypes = [vp, vp, vp]
     lib.skidgpu_set_groups.argtypes = [vp, vp, i, vp]
     lib.skidgpu_unbind.argtypes = [vp, f, f, d, i, f, i, i, i, vp, vp, P(i), P(i), P(i)]
@@ -84,8 +85,12 @@ def load_library():
     lib.skidgpu_stream.argtypes = [vp]
     lib.skidgpu_stream.restype = vp
     lib.skidgpu_set_reduce_cb.argtypes = [vp, vp, vp]
-    lib.skidgpu_mover_arrays.argtypes = [vp, P(vp), P(vp), P(vp), P(i), P(i), P(i)]
-    lib.skidgpu_mask_unowned_movers.argtypes = [vp]
+    lib.skidgpu_comm_unique_id.argtypes = [vp]
+    lib.skidgpu_comm_init.argtypes = [vp, vp, i, i]
+    lib.skidgpu_comm_bytes.argtypes = [vp, P(C.c_longlong)]
+    lib.skidgpu_comm_bytes.restype = C.c_longlong
+    lib.skidgpu_set_profile.argtypes = [vp, i]
+    lib.skidgpu_debug_move_kernel.argtypes = [vp, i]
     lib.skidgpu_debug_sort.argtypes = [vp, vp, vp, C.c_longlong, i]
     lib.skidgpu_debug_scan.argtypes = [vp, vp, vp, C.c_longlong]
     _lib = lib
@@ -101,6 +106,15 @@ def csmExp2Hub(dExp, H0, Omega0, Lambda, OmegaRad=0.0, Quintess=0.0):
 
 class SkidError(RuntimeError):
     pass
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 calls this, every rank passes it to SkidGPU.comm_init)."""
+    lib = load_library()
+    buf = (C.c_char * UNIQUE_ID_BYTES)()
+    if lib.skidgpu_comm_unique_id(C.cast(buf, C.c_void_p)) != 0:
+        raise SkidError(lib.skidgpu_last_error(None).decode())
+    return bytes(buf.raw)
 
 
 def _ptr(a):
@@ -161,16 +175,22 @@ class SkidGPU:
         self._reduce_cb = cfunc
         self._ck(self.lib.skidgpu_set_reduce_cb(self.h, C.cast(cfunc, C.c_void_p) if cfunc else None, None))
 
-    def mover_arrays(self):
-        px, py, pz = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        nm, lo, hi = C.c_int(0), C.c_int(0), C.c_int(0)
-        self._ck(self.lib.skidgpu_mover_arrays(self.h, C.byref(px), C.byref(py), C.byref(pz), C.byref(nm),
-                                               C.byref(lo), C.byref(hi)))
-        return px.value, py.value, pz.value, nm.value, lo.value, hi.value
+    def comm_init(self, unique_id, rank, nranks):
+        """NCCL communicator of this context (collective over all ranks); unique_id: 128 bytes from comm_unique_id()
+        of rank 0, handed over by any transport (torch.distributed broadcast, a file, MPI ...)."""
+        buf = (C.c_char * UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.skidgpu_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
 
-    def mask_unowned_movers(self):
-        """Zero the positions of movers other ranks own (then all-reduce(sum) the arrays)."""
-        self._ck(self.lib.skidgpu_mask_unowned_movers(self.h))
+    def comm_bytes(self):
+        nc = C.c_longlong(0)
+        b = self.lib.skidgpu_comm_bytes(self.h, C.byref(nc))
+        return int(b), int(nc.value)
+
+    def set_profile(self, on=True):
+        self._ck(self.lib.skidgpu_set_profile(self.h, int(on)))
+
+    def debug_move_kernel(self, which):
+        self._ck(self.lib.skidgpu_debug_move_kernel(self.h, which))
 
     def kdSetSoft(self, fEps):
         self._ck(self.lib.skidgpu_set_soft(self.h, fEps))
@@ -242,14 +262,15 @@ class SkidGPU:
         self._ck(self.lib.skidgpu_set_groups(self.h, _ptr(piGroup), nGroup, _ptr(centres)))
 
     def kdUnbind(self, G=1.0, z=0.0, fCosmo=0.0, iSoftType=SPLINE, fScoop=0.0, bNoUnbind=False, nMaxMembers=INT_MAX,
-                 nMinMembers=8):
-        grp = np.empty(self.n, np.int32)
-        cat = np.zeros(max(self.nGroup, 1), PGROUP_DTYPE)
+                 nMinMembers=8, fetch=True):
+        """fetch=False leaves labels and catalogue on the device (returned as None): counters only."""
+        grp = np.empty(self.n, np.int32) if fetch else None
+        cat = np.zeros(max(self.nGroup, 1), PGROUP_DTYPE) if fetch else None
         ng, nu, nb = C.c_int(0), C.c_int(0), C.c_int(0)
         self._ck(self.lib.skidgpu_unbind(self.h, G, z, fCosmo, iSoftType, fScoop, int(bNoUnbind), nMaxMembers,
                                          nMinMembers, _ptr(grp), _ptr(cat), C.byref(ng), C.byref(nu), C.byref(nb)))
         self.nGroup = ng.value
-        return grp, cat[:ng.value], nu.value, nb.value
+        return grp, (cat[:ng.value] if fetch else None), nu.value, nb.value
 
     def kdOutStats(self, G=1.0, z=0.0, fExpHub=0.0, fDensMin=0.0, fTempMax=FLT_MAX):
         """Accumulator rows behind the .stat file (kd.c:1703-1839), one per final group (row 0 unused)."""
@@ -289,7 +310,7 @@ def run_skid(pinit, nGas, nDark, nStar, tau, nSmooth=64, fDensMin=0.0, fTempMax=
              fCvg=None, fScoop=None, nMembers=8, nMaxMembers=INT_MAX, bNoUnbind=False, bGasAndDark=False,
              bGasOnly=False, bForceInitialCut=False, bNoPrune=False, period=None, center=(0.0, 0.0, 0.0),
              z=0.0, Omega0=1.0, Lambda=0.0, Quintess=0.0, G=1.0, H0=0.0, iSoftType=SPLINE, fEps=None, device=0,
-             want_arrays=True, ctx=None, want_stats=False):
+             want_arrays=True, ctx=None, want_stats=False, move_kernel=0):
     """The stage script of main.c:343-471 on one GPU.  Returns a dict of results."""
     tau = float(np.float32(tau))
     if fCvg is None:
@@ -303,6 +324,7 @@ def run_skid(pinit, nGas, nDark, nStar, tau, nSmooth=64, fDensMin=0.0, fTempMax=
     out = {}
     try:
         sk.log = []
+        sk.debug_move_kernel(move_kernel)
         sk.set_particles(pinit, nGas, nDark, nStar)
         rho, b2 = sk.smDensityInit(nSmooth, bGasAndDark, bGasOnly, want_arrays=want_arrays)
         out["rho"], out["ball2"], out["nExtraScat"] = rho, b2, sk.nExtraScat

@@ -2,7 +2,7 @@
 #include "ctx.cuh"
 #include <algorithm>
 
-cudaStream_t g_skid_stream = 0;
+thread_local cudaStream_t g_skid_stream = 0;
 
 #define API_BEGIN(ctx)                                                                                 \
 	if (!(ctx)) return SKIDGPU_ERR;                                                                \
@@ -47,9 +47,6 @@ extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPerio
 		c->bPeriodic = bPeriodic;
 		c->bDiag = bDiag;
 		CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-		CK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&c->evWalk0, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&c->evWalk1, cudaEventDisableTiming));
 		{ // keep freed blocks cached in the stream-ordered pool (DevBuf, common.cuh)
 			cudaMemPool_t pool;
 			unsigned long long keep = ~0ull;
@@ -58,8 +55,6 @@ extern "C" int skidgpu_create(skidgpu_ctx **pctx, int device, const float fPerio
 		}
 		CK(cudaEventCreate(&c->ev0));
 		CK(cudaEventCreate(&c->ev1));
-		CK(cudaEventCreate(&c->evk0));
-		CK(cudaEventCreate(&c->evk1));
 		*pctx = c;
 	} catch (const std::exception &e) {
 		g_create_err = e.what();
@@ -96,14 +91,9 @@ extern "C" void skidgpu_destroy(skidgpu_ctx *ctx)
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ev0) cudaEventDestroy(ctx->ev0);
 	if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-	if (ctx->evk0) cudaEventDestroy(ctx->evk0);
-	if (ctx->evk1) cudaEventDestroy(ctx->evk1);
-	if (ctx->evWalk0) cudaEventDestroy(ctx->evWalk0);
-	if (ctx->evWalk1) cudaEventDestroy(ctx->evWalk1);
-	if (ctx->stream2) {
-		cudaStreamSynchronize(ctx->stream2);
-		cudaStreamDestroy(ctx->stream2);
-	}
+	dist_comm_destroy(*ctx);
+	for (cudaEvent_t e : ctx->logEv) cudaEventDestroy(e);
+	if (ctx->hLog) cudaFreeHost(ctx->hLog);
 	cudaStream_t s = ctx->stream;
 	g_skid_stream = s;
 	delete ctx; // DevBuf destructors free on s
@@ -122,6 +112,48 @@ extern "C" int skidgpu_set_shard(skidgpu_ctx *ctx, int rank, int nranks)
 	if (nranks < 1 || rank < 0 || rank >= nranks) throw SkidError("skidgpu_set_shard: bad rank/nranks");
 	ctx->rank = rank;
 	ctx->nranks = nranks;
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_comm_unique_id(void *id128)
+{
+	try {
+		if (!id128) throw SkidError("skidgpu_comm_unique_id: null buffer");
+		dist_unique_id(id128);
+	} catch (const std::exception &e) {
+		g_create_err = e.what();
+		return SKIDGPU_ERR;
+	}
+	return SKIDGPU_OK;
+}
+
+extern "C" int skidgpu_comm_init(skidgpu_ctx *ctx, const void *id128, int rank, int nranks)
+{
+	API_BEGIN(ctx)
+	if (!id128 && nranks > 1) throw SkidError("skidgpu_comm_init: null unique id");
+	dist_comm_init(*ctx, id128, rank, nranks);
+	API_END(ctx)
+}
+
+extern "C" long long skidgpu_comm_bytes(skidgpu_ctx *ctx, long long *nCalls)
+{
+	if (!ctx) return -1;
+	if (nCalls) *nCalls = ctx->commCalls;
+	return ctx->commBytes;
+}
+
+extern "C" int skidgpu_set_profile(skidgpu_ctx *ctx, int bOn)
+{
+	API_BEGIN(ctx)
+	ctx->spans.on = bOn != 0;
+	API_END(ctx)
+}
+
+extern "C" int skidgpu_debug_move_kernel(skidgpu_ctx *ctx, int which)
+{
+	API_BEGIN(ctx)
+	if (which < 0 || which > 1) throw SkidError("skidgpu_debug_move_kernel: 0 = tiles, 1 = a tree walk per mover and step");
+	ctx->moveKernel = which;
 	API_END(ctx)
 }
 
@@ -356,25 +388,6 @@ extern "C" int skidgpu_get_moved(skidgpu_ctx *ctx, int *iOrder, float *r3)
 	API_END(ctx)
 }
 
-extern "C" int skidgpu_moved_dev(skidgpu_ctx *ctx, float **dxyz, int *nMove, int *lo, int *hi)
-{
-	API_BEGIN(ctx)
-	const int m = ctx->nMove;
-	float *b = ctx->mxyz.alloc((size_t)3 * (m > 0 ? m : 1));
-	cudaStream_t s = ctx->stream;
-	if (m > 0) {
-		CK(cudaMemcpyAsync(b, ctx->mx.p, sizeof(float) * m, cudaMemcpyDeviceToDevice, s));
-		CK(cudaMemcpyAsync(b + m, ctx->my.p, sizeof(float) * m, cudaMemcpyDeviceToDevice, s));
-		CK(cudaMemcpyAsync(b + 2 * (size_t)m, ctx->mz.p, sizeof(float) * m, cudaMemcpyDeviceToDevice, s));
-	}
-	CK(cudaStreamSynchronize(s));
-	if (dxyz) *dxyz = b;
-	if (nMove) *nMove = m;
-	if (lo) *lo = ctx->shardLo;
-	if (hi) *hi = ctx->shardHi;
-	API_END(ctx)
-}
-
 static void fetch_catalogue(skidgpu_ctx *ctx, int *piGroup, skidgpu_pgroup *g)
 {
 	cudaStream_t s = ctx->stream;
@@ -434,30 +447,9 @@ extern "C" int skidgpu_set_reduce_cb(skidgpu_ctx *ctx, skidgpu_reduce_cb cb, voi
 	API_END(ctx)
 }
 
-extern "C" int skidgpu_mask_unowned_movers(skidgpu_ctx *ctx)
-{
-	API_BEGIN(ctx)
-	move_mask_unowned(*ctx);
-	CK(cudaStreamSynchronize(ctx->stream));
-	API_END(ctx)
-}
-
-extern "C" int skidgpu_mover_arrays(skidgpu_ctx *ctx, float **dx, float **dy, float **dz, int *nMove, int *lo, int *hi)
-{
-	API_BEGIN(ctx)
-	CK(cudaStreamSynchronize(ctx->stream));
-	if (dx) *dx = ctx->mx.p;
-	if (dy) *dy = ctx->my.p;
-	if (dz) *dz = ctx->mz.p;
-	if (nMove) *nMove = ctx->nMove;
-	if (lo) *lo = ctx->shardLo;
-	if (hi) *hi = ctx->shardHi;
-	API_END(ctx)
-}
-
 extern "C" double skidgpu_kernel_ms(skidgpu_ctx *ctx, int which, int *nLaunches)
 {
-	if (!ctx || which < 0 || which > 1) return -1.0;
+	if (!ctx || which < 0 || which >= KF_COUNT) return -1.0;
 	if (nLaunches) *nLaunches = ctx->kernel_launches[which];
 	return ctx->kernel_ms[which];
 }

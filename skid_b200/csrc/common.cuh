@@ -27,7 +27,7 @@ struct SkidError : public std::runtime_error {
 	} while (0)
 
 // Launch counter (skidgpu_counter(…,0)): every kernel launch goes through SK_LAUNCH.
-extern long long g_skid_launches;
+extern thread_local long long g_skid_launches; // per host thread: one thread drives one context at a time
 #define SK_LAUNCH(kern, grid, block, smem, stream, ...)                                       \
 	do {                                                                                  \
 		kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                     \
@@ -35,20 +35,23 @@ extern long long g_skid_launches;
 		CK(cudaGetLastError());                                                       \
 	} while (0)
 
-// Grow-only device buffer, stream-ordered: cudaMallocAsync/cudaFreeAsync on the calling context's
-// stream (set by every API entry point) from the device's default pool, whose release threshold
+// Grow-only device buffer, stream-ordered: cudaMallocAsync on the calling context's stream (set per
+// HOST THREAD by every API entry point, so several contexts can be driven from several threads - one
+// thread per GPU in host/skid -gpus N) from the device's default pool, whose release threshold
 // skidgpu_create raises so that freed blocks stay cached - steady state does no driver allocation.
-extern cudaStream_t g_skid_stream;
+// A buffer is freed on the stream it was allocated on.
+extern thread_local cudaStream_t g_skid_stream;
 template <class T> struct DevBuf {
 	T *p = nullptr;
 	size_t cap = 0;
+	cudaStream_t owner = 0;
 	DevBuf() {}
 	DevBuf(const DevBuf &) = delete;
 	DevBuf &operator=(const DevBuf &) = delete;
 	~DevBuf() { release(); }
 	void release()
 	{
-		if (p) cudaFreeAsync(p, g_skid_stream);
+		if (p) cudaFreeAsync(p, owner);
 		p = nullptr;
 		cap = 0;
 	}
@@ -57,7 +60,8 @@ template <class T> struct DevBuf {
 		if (n > cap) {
 			release();
 			size_t want = n + n / 16 + 64;
-			CK(cudaMallocAsync((void **)&p, want * sizeof(T), g_skid_stream));
+			owner = g_skid_stream;
+			CK(cudaMallocAsync((void **)&p, want * sizeof(T), owner));
 			cap = want;
 		}
 		return p;
@@ -75,6 +79,10 @@ struct Workspace {
 	DevBuf<uint32_t> histScan;
 	DevBuf<uint64_t> keyAlt;
 	DevBuf<uint32_t> valAlt;
+	// distributed sort (tree.cu: dist_sort_pairs)
+	DevBuf<uint64_t> dsSamp, dsKey;
+	DevBuf<uint32_t> dsSampV, dsVal, dsFlag, dsScan;
+	DevBuf<int> dsCnt;
 };
 
 // out[0..n] = exclusive prefix sum of in[0..n) ; out has n+1 entries (out[n] = total).
@@ -101,8 +109,11 @@ struct BoxTree {
 // Sort n points (x,y,z arrays) by 63-bit Morton key; fills t.perm.  If lohi != nullptr it gives the
 // normalisation box (host floats lo[3],hi[3]) else the bounding box is reduced on the device.
 // radius (nullable): per-point ball radius; when given the sort key is (size class, Morton) - tree.cu.
+// dist (nullable): a context with nranks > 1 whose ranks all hold the same points - the sort is then shared
+// between the ranks (every rank sorts one key range, the pieces are all-gathered); same result.
+struct skidgpu_ctx;
 void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z, int n,
-                      Workspace &ws, cudaStream_t s, const float *radius = nullptr);
+                      Workspace &ws, cudaStream_t s, const float *radius = nullptr, skidgpu_ctx *dist = nullptr);
 void tree_bbox_only(BoxTree &t, const float *x, const float *y, const float *z, int n, cudaStream_t s);
 // Build the box levels over sorted points pos4[0..n) (xyz used).  infl (nullable): per-point
 // inflation radius (sorted order); aux (nullable): per-point value whose max goes to lo.w.

@@ -3,6 +3,59 @@
 #include "common.cuh"
 #include "../../include/skidgpu.h"
 
+// Device time per kernel family, measured with CUDA events on the context's stream WITHOUT synchronising the
+// host: spans are recorded while the work is enqueued and resolved (cudaEventElapsedTime) at the end of the
+// stage.  Enabled by skidgpu_set_profile (bench.py); off by default, the product path records nothing.
+enum { KF_TILE_STEP = 0, KF_KNN = 1, KF_BUILD = 2, KF_FALLBACK = 3, KF_PRUNE = 4, KF_COUNT = 5 };
+struct KernelSpans {
+	struct Span {
+		int fam;
+		size_t a, b;
+	};
+	std::vector<cudaEvent_t> ev;
+	std::vector<Span> spans;
+	size_t used = 0;
+	bool on = false;
+	cudaEvent_t next()
+	{
+		if (used == ev.size()) {
+			cudaEvent_t e;
+			CK(cudaEventCreate(&e));
+			ev.push_back(e);
+		}
+		return ev[used++];
+	}
+	void begin(int fam, cudaStream_t s)
+	{
+		if (!on) return;
+		spans.push_back({fam, used, 0});
+		CK(cudaEventRecord(next(), s));
+	}
+	void end(cudaStream_t s)
+	{
+		if (!on) return;
+		spans.back().b = used;
+		CK(cudaEventRecord(next(), s));
+	}
+	// after the stream has been synchronised: add the spans to ms[fam] / launches[fam]
+	void resolve(double *ms, int *cnt)
+	{
+		for (const Span &sp : spans) {
+			float t = 0;
+			if (cudaEventElapsedTime(&t, ev[sp.a], ev[sp.b]) == cudaSuccess) {
+				ms[sp.fam] += t;
+				++cnt[sp.fam];
+			}
+		}
+		spans.clear();
+		used = 0;
+	}
+	~KernelSpans()
+	{
+		for (cudaEvent_t e : ev) cudaEventDestroy(e);
+	}
+};
+
 struct skidgpu_ctx {
 	int device = 0;
 	cudaStream_t stream = 0;
@@ -10,7 +63,9 @@ struct skidgpu_ctx {
 	float L[3], C[3];
 	int bPeriodic = 0, bDiag = 0;
 	int rank = 0, nranks = 1;
-	skidgpu_reduce_cb reduceCb = nullptr;
+	void *comm = nullptr; // ncclComm_t of this context (dist.cu); null on one GPU
+	long long commBytes = 0, commCalls = 0;
+	skidgpu_reduce_cb reduceCb = nullptr; // test shim: exchanges through a host callback when no communicator is set
 	void *reduceUser = nullptr;
 
 	// ---- particles, SoA by iOrder (file order: gas, dark, star; kd.c:113-119)
@@ -55,11 +110,7 @@ struct skidgpu_ctx {
 	DevBuf<float> mx, my, mz, rox, roy, roz;
 	DevBuf<int> mOrd; // mover id -> iOrder
 	DevBuf<uint32_t> actList, actList2;
-	DevBuf<uint32_t> mList;            // candidate lists, LIST_CAP per mover (move.cu)
-	DevBuf<float> lx0, ly0, lz0, ldelta, lhmin;
-	DevBuf<int> lcnt;
-	float listInitFactor = 0.3f;
-	DevBuf<uint32_t> mQueue; // movers that refresh their list this step
+	DevBuf<uint32_t> mQueue; // movers that take this step with their own tree walk (move.cu)
 	// tiles: TILE consecutive entries of the position-sorted active list share one scatterer list (move.cu)
 	int nTiles = 0, tileStepsLeft = 0, tileWindow = 5, tileBuilds = 0, superCap = 2048;
 	DevBuf<uint64_t> tKeys;
@@ -68,13 +119,16 @@ struct skidgpu_ctx {
 	DevBuf<float4> tPos;
 	DevBuf<int> tCnt;
 	DevBuf<uint8_t> tPend;
-	int tileOverlap = 0;
-	cudaStream_t stream2 = 0; // k_tile_walk beside k_tile_step at a rebuild step (move.cu)
-	cudaEvent_t evWalk0 = nullptr, evWalk1 = nullptr;
 	DevBuf<uint32_t> supList;
 	DevBuf<int> supCnt;
 	DevBuf<uint32_t> tileQueue, shortQueue;
 	bool tileFresh = false;
+	int moveKernel = 0;    // test hook (skidgpu_debug_move_kernel): 0 tiles, 1 a tree walk per mover and step
+	int actPar = 0;        // which of the two device-side active counts (dT[8], dT[9]) is current
+	int nActiveBound = 0;  // host-side upper bound of the device-side active count (grid sizes)
+	uint32_t *hLog = nullptr; // pinned host mirror of the per-block log slots
+	DevBuf<uint32_t> dLog;
+	std::vector<cudaEvent_t> logEv;
 	DevBuf<float> tmpx, tmpy, tmpz;
 	BoxTree treeM;
 	DevBuf<uint32_t> dT; // [0] = T used this step (float bits), [1] = min rho of hit entities this step
@@ -85,7 +139,7 @@ struct skidgpu_ctx {
 	int shardLo = 0, shardHi = 0;
 	bool cyclic = false; // movers owned block-cyclically (move.cu) instead of [shardLo, shardHi)
 	int nOwned = 0;
-	DevBuf<float> mxyz; // contiguous x|y|z copy for the multi-GPU exchange
+	DevBuf<float> mxyz; // packed x|y|z blocks for the multi-GPU exchange of mover positions
 
 	// ---- groups
 	int nGroup = 0; // groups + 1 (kd->nGroup)
@@ -101,44 +155,22 @@ struct skidgpu_ctx {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	double stage_ms[6] = {0, 0, 0, 0, 0, 0};
 	long long nQueries = 0, nPairs = 0;
-	// dominant-kernel timing (skidgpu_kernel_ms)
-	cudaEvent_t evk0 = nullptr, evk1 = nullptr;
-	double kernel_ms[2] = {0, 0};
-	int kernel_launches[2] = {0, 0};
+	// kernel-family timing (skidgpu_kernel_ms)
+	KernelSpans spans;
+	double kernel_ms[KF_COUNT] = {0, 0, 0, 0, 0};
+	int kernel_launches[KF_COUNT] = {0, 0, 0, 0, 0};
 };
 
-// Brackets a group of launches of one dominant kernel with events; stop() must be called after a
-// stream synchronisation point has been reached (it synchronises on the stop event itself).
-struct KernelTimer {
-	skidgpu_ctx &c;
-	int which;
-	bool open = false;
-	KernelTimer(skidgpu_ctx &c_, int w) : c(c_), which(w) {}
-	void start()
-	{
-		CK(cudaEventRecord(c.evk0, c.stream));
-		open = true;
-	}
-	void stop(int launches)
-	{
-		if (!open) return;
-		CK(cudaEventRecord(c.evk1, c.stream));
-		CK(cudaEventSynchronize(c.evk1));
-		float ms = 0;
-		CK(cudaEventElapsedTime(&ms, c.evk0, c.evk1));
-		c.kernel_ms[which] += ms;
-		c.kernel_launches[which] += launches;
-		open = false;
-	}
-};
-
-// multi-GPU agreement point (no-op on one rank)
-static inline void sk_reduce(skidgpu_ctx &c, void *dev, long long count, int dtype, int op)
-{
-	if (c.nranks <= 1) return;
-	if (!c.reduceCb) throw SkidError("nranks > 1 but no reduce callback set (skidgpu_set_reduce_cb)");
-	if (c.reduceCb(c.reduceUser, dev, count, dtype, op) != 0) throw SkidError("reduce callback failed");
-}
+// multi-GPU exchange points (dist.cu); no-ops on one rank
+void sk_reduce(skidgpu_ctx &c, void *dev, long long count, int dtype, int op);
+void sk_allgather(skidgpu_ctx &c, void *buf, long long per, int dtype);
+void sk_allgatherv(skidgpu_ctx &c, const void *send, void *recv, const long long *counts, const long long *offs, int dtype);
+void dist_unique_id(void *id128);
+void dist_comm_init(skidgpu_ctx &c, const void *id128, int rank, int nranks);
+void dist_comm_destroy(skidgpu_ctx &c);
+// stable sort of (key, val) pairs that every rank holds identically: each rank sorts one key range, the pieces
+// are all-gathered (tree.cu).  Only vals[] is sorted on return (keys[] is scratch).  radix_sort_pairs on one rank.
+void dist_sort_pairs(skidgpu_ctx &c, uint64_t *keys, uint32_t *vals, size_t n, int bits);
 #define SK_I32 0
 #define SK_U8 1
 #define SK_F32 2
@@ -152,7 +184,6 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
                 int bForceInitialCut, int bNoPrune, skidgpu_log_cb cb, void *user, int *nMove, int *nIttr);
 void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb, void *user);
-void move_mask_unowned(skidgpu_ctx &c); // zero the positions of movers other ranks own (before the sum-exchange)
 void stage_fof(skidgpu_ctx &c, float fTau, int *nGroup);
 void stage_centers(skidgpu_ctx &c);
 void stage_set_groups(skidgpu_ctx &c, const int *piGroup, int nGroup, const skidgpu_pgroup *centres);

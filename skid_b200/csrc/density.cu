@@ -10,6 +10,7 @@
 // staged in a 64-entry shared-memory buffer and merged 32 at a time with bitonic networks.
 // The result is the k smallest by (d2, tree index): deterministic, independent of visit order.
 #include "ctx.cuh"
+#include <algorithm>
 
 // ------------------------------------------------------------------ species rules
 // ScatterCriterion (kd.c:600-627).  type by iOrder range (kdParticleType, kd.c:113-119).
@@ -502,7 +503,7 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	SK_LAUNCH(k_gather3, (unsigned)ceil_div(m, 256), 256, 0, s, m, actIdx, c.x.p, c.y.p, c.z.p, gx, gy, gz);
 
 	// tree over the active set (kdBuildTree)
-	tree_sort_points(c.treeA, gx, gy, gz, m, c.ws, s);
+	tree_sort_points(c.treeA, gx, gy, gz, m, c.ws, s, nullptr, &c);
 	float4 *posA = c.posA.alloc(m);
 	int *iordA = c.iordA.alloc(m);
 	SK_LAUNCH(k_gather_sortedA, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeA.perm.p, actIdx, c.x.p, c.y.p,
@@ -522,24 +523,24 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 		ka.boxLo[d] = c.bPeriodic ? (float)((double)c.C[d] - 0.5 * (double)c.L[d]) : -3.4e38f;
 		ka.boxHi[d] = c.bPeriodic ? (float)((double)c.C[d] + 0.5 * (double)c.L[d]) : 3.4e38f;
 	}
-	ka.ball2 = c.ball2A.alloc(m);
+	// multi-GPU: queries are sharded by contiguous Morton ranges of equal length; fBall2 has one writer per entry
+	// (all-gather), the f64 density partials scatter onto neighbours of other ranges (all-reduce sum), so every
+	// rank ends with identical arrays
+	const int chunk = (int)ceil_div(m, c.nranks);
+	ka.ball2 = c.ball2A.alloc((size_t)chunk * c.nranks);
 	ka.rho64 = c.rho64A.alloc(m);
 	ka.nbr = c.keepNbr ? c.nbr.p : nullptr;
 	ka.nbrD2 = c.keepNbr ? c.nbrD2.p : nullptr;
 	CK(cudaMemsetAsync(ka.rho64, 0, sizeof(double) * m, s));
-	CK(cudaMemsetAsync(ka.ball2, 0, sizeof(float) * m, s));
-	// multi-GPU: queries are sharded by contiguous Morton ranges; fBall2 (one writer per entry) and the
-	// f64 density partials are summed across ranks, so every rank ends with identical arrays
-	ka.qLo = (int)((long long)m * c.rank / c.nranks);
-	ka.qHi = (int)((long long)m * (c.rank + 1) / c.nranks);
-	KernelTimer kt(c, 1);
-	c.kernel_ms[1] = 0;
-	c.kernel_launches[1] = 0;
-	kt.start();
+	ka.qLo = std::min(m, chunk * c.rank);
+	ka.qHi = std::min(m, chunk * (c.rank + 1));
+	c.kernel_ms[KF_KNN] = 0;
+	c.kernel_launches[KF_KNN] = 0;
+	c.spans.begin(KF_KNN, s);
 	if (ka.qHi > ka.qLo)
 		SK_LAUNCH(k_knn_density, (unsigned)ceil_div(ka.qHi - ka.qLo, KNN_WARPS), KNN_WARPS * 32, 0, s, ka);
-	kt.stop(1);
-	sk_reduce(c, ka.ball2, m, SK_F32, SK_SUM);
+	c.spans.end(s);
+	sk_allgather(c, ka.ball2, chunk, SK_F32);
 	sk_reduce(c, ka.rho64, m, SK_F64, SK_SUM);
 	c.nQueries += ka.qHi - ka.qLo;
 	float *rhoA = c.rhoA.alloc(m);
@@ -585,7 +586,7 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 		}
 	SK_LAUNCH(k_replicas<1>, (unsigned)ceil_div(m, 256), 256, 0, s, ra, nullptr, scan, posU, nrU, srcU, ex, ey, ez,
 	          einfl);
-	tree_sort_points(c.treeE, ex, ey, ez, ne, c.ws, s);
+	tree_sort_points(c.treeE, ex, ey, ez, ne, c.ws, s, nullptr, &c);
 	float4 *ep = c.entPos.alloc(ne + 64);
 	float4 *enr = c.entNR.alloc(ne + 64);
 	uint32_t *esrc = c.entSrc.alloc(ne);
@@ -599,4 +600,5 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	tree_build_boxes(c.treeE, ep, inflS, rhoS, ne, s, 32, 32);
 	CK(cudaMemsetAsync(c.entTouched.alloc(ne + 64), 0, ne + 64, s));
 	tm.stop();
+	c.spans.resolve(c.kernel_ms, c.kernel_launches);
 }

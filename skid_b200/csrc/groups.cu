@@ -768,9 +768,16 @@ __global__ void __launch_bounds__(256) k_cat_pack(int nGroup, const skidgpu_pgro
 		o[1 + j] = own ? cat[g].vcm[j] : 0.0f;
 		o[4 + j] = own ? cat[g].rBound[j] : 0.0f;
 	}
-	o[7] = own ? (float)gN[g] : 0.0f;
+	o[7] = 0.0f;
 }
-__global__ void __launch_bounds__(256) k_cat_unpack(int nGroup, skidgpu_pgroup *cat, int *gN, const float *f)
+// member counts travel as integers (a float row entry is exact only up to 2^24 members)
+__global__ void __launch_bounds__(256) k_count_pack(int nGroup, const int *gN, int rank, int nranks, int *out)
+{
+	int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= nGroup) return;
+	out[g] = (g > 0 && (g % nranks) == rank) ? gN[g] : 0;
+}
+__global__ void __launch_bounds__(256) k_cat_unpack(int nGroup, skidgpu_pgroup *cat, int *gN, const float *f, const int *cnt)
 {
 	int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= nGroup || g == 0) return;
@@ -780,7 +787,7 @@ __global__ void __launch_bounds__(256) k_cat_unpack(int nGroup, skidgpu_pgroup *
 		cat[g].vcm[j] = o[1 + j];
 		cat[g].rBound[j] = o[4 + j];
 	}
-	gN[g] = (int)(o[7] + 0.5f);
+	gN[g] = cnt[g];
 	cat[g].nMembers = gN[g];
 }
 
@@ -872,7 +879,7 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 		SK_LAUNCH(k_gid_keys, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, keys.p, order.p);
 		int bits = 1;
 		while ((1ll << bits) < (long long)G) ++bits;
-		radix_sort_pairs(keys.p, order.p, n, bits, c.ws, s);
+		dist_sort_pairs(c, keys.p, order.p, n, bits); // replicated input: shared between the ranks
 		cntU.alloc(G + 2);
 		uint32_t *scan = c.scan.alloc((size_t)(G > n ? G : n) + 64);
 		SK_LAUNCH(k_copy_counts, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, cntU.p);
@@ -893,7 +900,7 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			sz.alloc(n0);
 			SK_LAUNCH(k_gather_scoop_src, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, order.p, c.x.p, c.y.p, c.z.p, sx.p,
 			          sy.p, sz.p);
-			tree_sort_points(treeS, sx.p, sy.p, sz.p, n0, c.ws, s);
+			tree_sort_points(treeS, sx.p, sy.p, sz.p, n0, c.ws, s, nullptr, &c);
 			SK_LAUNCH(k_gather_scoop_sorted, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, treeS.perm.p, order.p, c.x.p,
 			          c.y.p, c.z.p, c.mass.p, c.soft.p, posS.p, softS.p);
 			tree_build_boxes(treeS, posS.p, nullptr, nullptr, n0, s);
@@ -1013,11 +1020,15 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			SK_LAUNCH(k_unbind, (unsigned)(G - 1), UNB_T, 0, s, ua);
 			if (c.nranks > 1) { // merge the shards: labels (owner wrote 0 for unbound members), rows, count
 				DevBuf<float> pack;
+				DevBuf<int> cpack;
 				pack.alloc((size_t)G * 8);
+				cpack.alloc((size_t)G + 1);
 				sk_reduce(c, c.gid.p, n, SK_I32, SK_MIN);
 				SK_LAUNCH(k_cat_pack, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gCat.p, c.gN.p, c.rank, c.nranks, pack.p);
+				SK_LAUNCH(k_count_pack, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, c.rank, c.nranks, cpack.p);
 				sk_reduce(c, pack.p, (long long)G * 8, SK_F32, SK_SUM);
-				SK_LAUNCH(k_cat_unpack, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gCat.p, c.gN.p, pack.p);
+				sk_reduce(c, cpack.p, G, SK_I32, SK_SUM);
+				SK_LAUNCH(k_cat_unpack, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gCat.p, c.gN.p, pack.p, cpack.p);
 				sk_reduce(c, dCnt.p, 1, SK_I32, SK_SUM);
 				CK(cudaStreamSynchronize(s));
 			}

@@ -16,6 +16,7 @@
 #include <utility>
 
 #define T_NONE 0x7f800000u // +inf bits: "no entity was hit this step"
+#define DT_NACT_HOST 8     // = DT_NACT (the enum follows StepArgs)
 
 
 // CutCriterion (kd.c:555-597)
@@ -72,8 +73,7 @@ __global__ void __launch_bounds__(256) k_gather3b(int m, const uint32_t *idx, co
 // movers in Morton order: r = rOld = initial position, mOrd = iOrder (kd.c:653-662)
 __global__ void __launch_bounds__(256)
     k_init_movers(int m, const uint32_t *perm, const uint32_t *fileIdx, const float *x, const float *y,
-                  const float *z, float *mx, float *my, float *mz, float *rox, float *roy, float *roz, int *mOrd,
-                  const float *ball2, float *lhmin, int *lcnt, float initFactor)
+                  const float *z, float *mx, float *my, float *mz, float *rox, float *roy, float *roz, int *mOrd)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m) return;
@@ -86,8 +86,6 @@ __global__ void __launch_bounds__(256)
 	roy[i] = py;
 	roz[i] = pz;
 	mOrd[i] = (int)j;
-	lhmin[i] = initFactor * sqrtf(fmaxf(ball2[j], 0.0f)); // first margin: a fraction of the mover's own ball radius
-	lcnt[i] = -1;
 }
 
 __global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
@@ -100,22 +98,16 @@ __global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
 // movers belongs to rank j % nranks).  Contiguous ranges put whole halos on one rank, and the ranks that
 // converged early then wait at every step's agreement point for the one that holds the largest halo
 // (measured on 2 GPUs: move 447 ms against 290 ms ideal); interleaved blocks give every rank a
-// statistically identical sample.
-constexpr int OWN_BLOCK = 256;
+// statistically identical sample.  The blocks are large (4096 Morton-consecutive movers = 128 supertiles):
+// with 256 every rank touched every scatterer of the box (the lists of neighbouring blocks overlap almost
+// completely), which cost the step kernel a third of its speed at 8 ranks.
+constexpr int OWN_BLOCK = 4096;
 __global__ void __launch_bounds__(256) k_owned_ids(int rank, int nranks, int own, uint32_t *out)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= own) return;
 	const int lb = i / OWN_BLOCK, off = i % OWN_BLOCK;
 	out[i] = (uint32_t)((lb * nranks + rank) * OWN_BLOCK + off);
-}
-__global__ void __launch_bounds__(256) k_mask_unowned(int m, int rank, int nranks, float *x, float *y, float *z)
-{
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= m || (i / OWN_BLOCK) % nranks == rank) return;
-	x[i] = 0.0f;
-	y[i] = 0.0f;
-	z[i] = 0.0f;
 }
 static int owned_count(int m, int rank, int nranks)
 {
@@ -124,28 +116,61 @@ static int owned_count(int m, int rank, int nranks)
 	for (int j = rank; j < nb; j += nranks) own += (j == nb - 1) ? m - j * OWN_BLOCK : OWN_BLOCK;
 	return own;
 }
-// all owned movers active, in mover order
-static void init_active_list(skidgpu_ctx &c)
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
+// Exchange of mover positions (before FoF and before the centres every rank needs every mover):
+// the owned blocks are packed into this rank's slot of one buffer (x | y | z planes), all-gathered in place
+// and unpacked - 12 bytes per mover on the wire, one collective.
+__global__ void __launch_bounds__(256)
+    k_pack_owned(int m, int rank, int nranks, int perBlocks, const float *x, const float *y, const float *z, float *buf)
 {
-	if (c.nActive <= 0) return;
-	if (c.cyclic)
-		SK_LAUNCH(k_owned_ids, (unsigned)ceil_div(c.nActive, 256), 256, 0, c.stream, c.rank, c.nranks, c.nActive,
-		          c.actList.p);
-	else SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nActive, 256), 256, 0, c.stream, c.shardLo, c.nActive, c.actList.p);
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; // index within this rank's slot plane
+	if (i >= (size_t)perBlocks * OWN_BLOCK) return;
+	const size_t lb = i / OWN_BLOCK, off = i % OWN_BLOCK;
+	const size_t id = (lb * nranks + rank) * OWN_BLOCK + off;
+	const size_t plane = (size_t)perBlocks * OWN_BLOCK;
+	float *o = buf + (size_t)rank * 3 * plane;
+	const bool ok = id < (size_t)m;
+	o[i] = ok ? x[id] : 0.0f;
+	o[plane + i] = ok ? y[id] : 0.0f;
+	o[2 * plane + i] = ok ? z[id] : 0.0f;
 }
-void move_mask_unowned(skidgpu_ctx &c)
+__global__ void __launch_bounds__(256)
+    k_unpack_all(int m, int rank, int nranks, int perBlocks, const float *buf, float *x, float *y, float *z)
+{
+	const size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= (size_t)m) return;
+	const size_t blk = id / OWN_BLOCK, off = id % OWN_BLOCK;
+	const int r = (int)(blk % nranks);
+	if (r == rank) return;
+	const size_t plane = (size_t)perBlocks * OWN_BLOCK;
+	const float *o = buf + (size_t)r * 3 * plane + (blk / nranks) * OWN_BLOCK + off;
+	x[id] = o[0];
+	y[id] = o[plane];
+	z[id] = o[2 * plane];
+}
+static void exchange_positions(skidgpu_ctx &c)
 {
 	if (c.nranks <= 1 || c.nMove <= 0) return;
-	if (!c.cyclic) {
-		const int m = c.nMove, lo = c.shardLo, hi = c.shardHi;
-		for (float *p : {c.mx.p, c.my.p, c.mz.p}) {
-			if (lo > 0) CK(cudaMemsetAsync(p, 0, sizeof(float) * lo, c.stream));
-			if (hi < m) CK(cudaMemsetAsync(p + hi, 0, sizeof(float) * (m - hi), c.stream));
-		}
-		return;
-	}
-	SK_LAUNCH(k_mask_unowned, (unsigned)ceil_div(c.nMove, 256), 256, 0, c.stream, c.nMove, c.rank, c.nranks, c.mx.p,
-	          c.my.p, c.mz.p);
+	const int m = c.nMove;
+	const int nb = (int)ceil_div(m, OWN_BLOCK), perBlocks = (int)ceil_div(nb, c.nranks);
+	const size_t plane = (size_t)perBlocks * OWN_BLOCK;
+	float *buf = c.mxyz.alloc(3 * plane * c.nranks);
+	SK_LAUNCH(k_pack_owned, (unsigned)ceil_div(plane, 256), 256, 0, c.stream, m, c.rank, c.nranks, perBlocks, c.mx.p, c.my.p,
+	          c.mz.p, buf);
+	sk_allgather(c, buf, (long long)(3 * plane), SK_F32);
+	SK_LAUNCH(k_unpack_all, (unsigned)ceil_div(m, 256), 256, 0, c.stream, m, c.rank, c.nranks, perBlocks, buf, c.mx.p, c.my.p,
+	          c.mz.p);
+}
+// all owned movers active, in mover order; the device-side count follows
+static void init_active_list(skidgpu_ctx &c)
+{
+	c.nActiveBound = c.nOwned;
+	SK_LAUNCH(k_set_u32, 1, 1, 0, c.stream, c.dT.p + DT_NACT_HOST + c.actPar, (uint32_t)c.nOwned);
+	if (c.nOwned <= 0) return;
+	if (c.nranks > 1)
+		SK_LAUNCH(k_owned_ids, (unsigned)ceil_div(c.nOwned, 256), 256, 0, c.stream, c.rank, c.nranks, c.nOwned, c.actList.p);
+	else SK_LAUNCH(k_iota, (unsigned)ceil_div(c.nOwned, 256), 256, 0, c.stream, 0, c.nOwned, c.actList.p);
 }
 
 struct StepArgs {
@@ -156,23 +181,14 @@ struct StepArgs {
 	uint8_t *touched;     // nullable: set for entities with >= 1 hit (step 0, initial cut)
 	float *mx, *my, *mz;
 	const uint32_t *act;
-	int nActive;
+	int par;  // the current active count lives on the device: dT[8 + par] (the host only knows an upper bound)
 	int nEnt;
-	uint32_t *dT; // [0] threshold T (float bits), [1] running min of rho over hit entities (float bits)
+	uint32_t *dT; // [0] threshold T (float bits), [1] running min of rho over hit entities (float bits); see DT_*
 	float fStep;
 	float L[3];
 	double wrapLo[3], wrapHi[3];
 	float *a0x, *a0y, *a0z; // nullable: keep accelerations
-	// candidate lists (k_move_list): per mover LIST_CAP scatterer indices, list origin, margin,
-	// count (-1 = no valid list), and the smallest containing ball radius seen at the last walk
-	uint32_t *list;
-	uint32_t listBase; // first mover id of this shard
-	float *lx0, *ly0, *lz0, *ldelta, *lhmin;
-	int *lcnt;
-	int walkAlways; // debug (SKIDGPU_LIST_WALK_ALWAYS=1): never use the lists
-	float polShrink, polGrow; // margin feedback (see k_move_list)
-	int polGrowMax;
-	uint32_t *queue;      // movers whose list must be refreshed this step
+	uint32_t *queue;      // movers that take this step with their own tree walk (left their tile's reach)
 	uint32_t *queueCount; // = dT + 2, reset by k_update_T
 	float wrapHiF[3], wrapLoF[3]; // largest floats <= wrapHi / wrapLo: same decisions as the double compares
 	// tiles (k_tile_build / k_tile_step): TILE consecutive entries of the position-sorted active list
@@ -187,9 +203,11 @@ struct StepArgs {
 	uint32_t *supList; // supCap per supertile (scratch between k_super_walk and k_tile_filter)
 	int *supCnt;
 	int supCap;
-	uint8_t *tPend; // per tile: 1 = queued for k_tile_walk at this rebuild (k_tile_filter)
-	int walkDyn; // k_tile_walk takes its tiles from a ticket counter (dT[7]) instead of a static round-robin
 };
+// device-side counters of the move loop (uint32 words of dT)
+enum { DT_T = 0, DT_MIN = 1, DT_QUEUE = 2, DT_TILEQ = 3, DT_SHORTQ = 5, DT_BIG = 6, DT_TICKET = 7, DT_NACT = 8 /* and 9 */,
+       DT_STEPS = 12 /* 64-bit: mover-steps of this stage */, DT_WORDS = 16 };
+#define N_ACTIVE(a) ((int)(a).dT[DT_NACT + (a).par])
 
 // kdMoveParticles (kd.c:711-729) for one mover.  The reference forms ai = fStep/sqrt(|a|^2) in double and
 // rounds it to float; here a refined float reciprocal square root gives the same value to <= 2 ulp
@@ -243,31 +261,6 @@ __device__ __forceinline__ void move_one(const StepArgs &a, uint32_t id, float x
 }
 
 
-// Default kernels: per-mover candidate lists ("Verlet lists").
-//
-// ncu on the v1 kernel above (profiles/r01_v1_move_*): issue-bound, ~3600 warp instructions per
-// mover-step, of which ~85 % are tree bookkeeping and misses (1500 scatterers tested for 85 hits).
-// A mover travels exactly fStep (= tau/4) per step while the balls that contain it have radii of
-// many tau, so the set of scatterers that CAN contain it changes slowly.  Each mover keeps the list
-// of scatterers e with |x_e - x0| < h_e + delta collected by one tree walk at x0; while it stays
-// within delta of x0 every scatterer that contains it is in the list (triangle inequality), and a
-// step only reads the list, gathers those scatterers and runs the SAME float32 hit test.
-//
-//  * k_list_eval   (every step, one warp per active mover, small register footprint -> full
-//                   occupancy; it is latency bound): movers with a valid list take their step;
-//                   the others are appended to a refresh queue.
-//  * k_list_refresh(every step, one warp per queued mover): walks the tree, evaluating this step
-//                   and emitting the new list in the same pass.  Leaf buckets are fetched two at a
-//                   time to keep more loads in flight.
-//
-// Splitting the two keeps warps that run ~10x longer out of the blocks of the short ones.  The margin
-// delta is feedback-controlled per mover (tools/sweep_policy.sh).  The hit set, the hit test and the
-// pruning rule are exactly those of v1 (verified against it and against the reference: same groups,
-// same Ittr trace).  A periodic wrap moves the mover by L, which fails the drift check by construction.
-constexpr int LIST_CAP = 384;
-constexpr int EVAL_WARPS = 4;
-constexpr int REFRESH_WARPS = 4;
-
 // the end of every step for one mover (one thread): min density of the scatterers that hit it, optional
 // copy of the acceleration, kdMoveParticles
 __device__ __forceinline__ void finish_mover(const StepArgs &a, uint32_t id, float x, float y, float z, float ax,
@@ -297,66 +290,6 @@ __device__ __forceinline__ void finish_step(const StepArgs &a, uint32_t id, floa
 		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
 	}
 	if (lane == 0) finish_mover(a, id, x, y, z, ax, ay, az, rmin);
-}
-
-// One list entry: the reference's float32 hit test (smBallGather, smooth1.c:365-369: dx = x_scatterer -
-// x_mover, no FMA) and, on a hit, smAccDensity.
-#define EVAL_ENTRY(p, q)                                                                               \
-	{                                                                                              \
-		const float dx = __fsub_rn((p).x, x), dy = __fsub_rn((p).y, y), dz = __fsub_rn((p).z, z); \
-		const float d2 = dist2_rn(dx, dy, dz);                                                 \
-		if (d2 < (p).w && (q).z >= T) ACC_HIT(dx, dy, dz, d2, q);                              \
-	}
-
-// ncu on the first split version (profiles/r01_v3_eval_*): no unit busy, 34 stall cycles per issued
-// instruction on the dependent chain active list -> mover state -> list -> scatterer records, each
-// hop a full L2/DRAM latency.  Here the first list chunk is requested together with the mover state
-// (its address depends only on the mover id; stale or unused slots are clamped to valid indices), and
-// the list is consumed 64 entries at a time with the index loads of the next chunk and both record
-// gathers of this chunk in flight before the first use.
-__global__ void __launch_bounds__(EVAL_WARPS * 32, 10) k_list_eval(const StepArgs a)
-{
-	const int lane = threadIdx.x & 31;
-	const int wi = blockIdx.x * EVAL_WARPS + (threadIdx.x >> 5);
-	if (wi >= a.nActive) return;
-	const uint32_t id = a.act[wi];
-	const uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP;
-	const uint32_t emax = (uint32_t)a.nEnt - 1u;
-	uint32_t ea = list[lane], eb = list[32 + lane];
-	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
-	const int cnt0 = a.lcnt[id];
-	const float ox = x - a.lx0[id], oy = y - a.ly0[id], oz = z - a.lz0[id];
-	const float dl = a.ldelta[id];
-	const float T = __uint_as_float(a.dT[0]);
-	const bool useList = cnt0 >= 0 && !a.walkAlways && (ox * ox + oy * oy + oz * oz) * 1.0001f <= dl * dl;
-	if (!useList) { // drifted past the margin (or no list yet): the refresh kernels take this step
-		if (lane == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id;
-		return;
-	}
-	float ax = 0.0f, ay = 0.0f, az = 0.0f;
-	float rmin = 3.0e38f;
-	for (int s0 = 0; s0 < cnt0; s0 += 64) {
-		// both halves of a scatterer's 32-byte record (one sector) are fetched together
-		ea = min(ea, emax);
-		float4 pa = a.entRec[2 * (size_t)ea];
-		const float4 qa = a.entRec[2 * (size_t)ea + 1];
-		const bool two = s0 + 32 < cnt0;
-		float4 pb = make_float4(0.0f, 0.0f, 0.0f, -1.0f), qb = pb;
-		if (two) {
-			eb = min(eb, emax);
-			pb = a.entRec[2 * (size_t)eb];
-			qb = a.entRec[2 * (size_t)eb + 1];
-		}
-		if (s0 + 64 < cnt0) { // cnt0 <= LIST_CAP, a multiple of 64
-			ea = list[s0 + 64 + lane];
-			eb = list[s0 + 96 + lane];
-		}
-		if (s0 + lane >= cnt0) pa.w = -1.0f;
-		if (s0 + 32 + lane >= cnt0) pb.w = -1.0f;
-		EVAL_ENTRY(pa, qa);
-		if (two) EVAL_ENTRY(pb, qb);
-	}
-	finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,9 +345,6 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 		}                                                                                      \
 	}
 constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
-constexpr int TILEWALK_DYN_DEFAULT = 1; // measured with OCC 8: move 292 -> 288 ms gas+dark, 231 -> 215 ms massive
-constexpr int TILE_OVERLAP_DEFAULT = 0;
-constexpr int TILEWALK_OCC_DEFAULT = 8; // measured (tools/ab_probe.py, 2^24): move 300 -> 291 ms gas+dark, 257 -> 230 ms massive
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
 {
@@ -428,11 +358,16 @@ __device__ __forceinline__ uint64_t spread21m(uint32_t v)
 }
 
 // 63-bit Morton key of the current position of every active mover (bbox = box of the initial positions)
-__global__ void __launch_bounds__(256) k_mover_keys(int nActive, const uint32_t *act, const float *mx, const float *my,
+__global__ void __launch_bounds__(256) k_mover_keys(int bound, const uint32_t *dN, const uint32_t *act, const float *mx, const float *my,
                                                     const float *mz, const float *bbox, uint64_t *keys, uint32_t *vals)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= nActive) return;
+	if (i >= bound) return;
+	if (i >= (int)*dN) { // beyond the device-side count (the host's bound is stale): sorts to the end
+		keys[i] = ~0ull;
+		vals[i] = 0u;
+		return;
+	}
 	const uint32_t id = act[i];
 	const float p[3] = {mx[id], my[id], mz[id]};
 	uint32_t q[3];
@@ -479,19 +414,16 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint32_t nq = *queueCount;
 	const float T = __uint_as_float(a.dT[0]);
-	// the queued tiles differ a lot in cost (dense cores): with walkDyn a warp draws its next tile from a ticket
-	// counter (reset by k_update_T at the end of every step; one launch of this kernel per step)
-	uint32_t wi = blockIdx.x * 4 + (threadIdx.x >> 5);
-	if (a.walkDyn) {
-		if (lane == 0) wi = atomicAdd(a.dT + 7, 1u);
-		wi = __shfl_sync(SK_FULL, wi, 0);
-	}
+	const int nActive = N_ACTIVE(a);
+	// the queued tiles differ a lot in cost (dense cores): a warp draws its next tile from a ticket counter
+	// (reset by k_update_T at the end of every step; one launch of this kernel per step)
+	uint32_t wi = 0;
+	if (lane == 0) wi = atomicAdd(a.dT + DT_TICKET, 1u);
+	wi = __shfl_sync(SK_FULL, wi, 0);
 	for (; wi < nq;) {
 		const int t = (int)queue[wi];
-		if (a.walkDyn) {
-			if (lane == 0) wi = atomicAdd(a.dT + 7, 1u);
-			wi = __shfl_sync(SK_FULL, wi, 0);
-		} else wi += gridDim.x * 4;
+		if (lane == 0) wi = atomicAdd(a.dT + DT_TICKET, 1u);
+		wi = __shfl_sync(SK_FULL, wi, 0);
 		uint32_t off = (uint32_t)t * TILE_CAP;
 		uint32_t *list = a.tList + off;
 		int cap = TILE_CAP;
@@ -499,7 +431,7 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 		float amax = 0.0f;
 #pragma unroll
 		for (int m = 0; m < TILE; ++m) {
-			const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
+			const uint32_t id = a.act[min(t * TILE + m, nActive - 1)]; // a short last tile repeats its last member
 			mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
 			amax = fmaxf(amax, fmaxf(fabsf(mxv[m]), fmaxf(fabsf(myv[m]), fabsf(mzv[m]))));
 		}
@@ -566,7 +498,7 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 #undef TILE_TEST_CHILDREN
 			if (!overflow && attempt == 1 && shortQueue && lane == 0) shortQueue[atomicAdd(shortCount, 1u)] = (uint32_t)t;
 		}
-		if (!overflow && lane < TILE && t * TILE + lane < a.nActive) { // where the list was built and how far it reaches
+		if (!overflow && lane < TILE && t * TILE + lane < nActive) { // where the list was built and how far it reaches
 			float px = mxv[0], py = myv[0], pz = mzv[0];
 #pragma unroll
 			for (int m = 1; m < TILE; ++m)
@@ -589,16 +521,17 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 //    tree walks, and the expensive test runs on ~1000 entries instead of ~6000.
 // Supertiles whose superset overflows (members far apart) fall back to tile_walk in k_tile_filter.
 constexpr int SUPER = 32 / TILE;
-constexpr int SUPER_CAP = 2048; // default superset capacity per supertile (ctx.superCap, SKIDGPU_SUPER_CAP)
-__global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper, float reach)
+constexpr int SUPER_CAP = 2048; // superset capacity per supertile (3072/4096/6144 measured: +-1 %, 6144 slower)
+__global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, float reach)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1u;
 	const int st = blockIdx.x * 4 + (threadIdx.x >> 5);
-	if (st >= nSuper) return;
+	const int nActive = N_ACTIVE(a);
+	if (st * 32 >= nActive) return;
 	const float T = __uint_as_float(a.dT[0]);
 	const int mi = st * 32 + lane;
-	const uint32_t id = a.act[min(mi, a.nActive - 1)]; // a short last supertile repeats the last mover
+	const uint32_t id = a.act[min(mi, nActive - 1)]; // a short last supertile repeats the last mover
 	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
 	float x0 = x, x1 = x, y0 = y, y1 = y, z0 = z, z1 = z;
 #pragma unroll
@@ -615,7 +548,7 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper
 	const float r = reach * 1.001f + 4.0e-7f * fmaxf(fmaxf(fabsf(x0), fabsf(x1)),
 	                                                 fmaxf(fmaxf(fabsf(y0), fabsf(y1)), fmaxf(fabsf(z0), fabsf(z1))));
 	const float r2 = r * r;
-	if (mi < a.nActive) a.tPos[mi] = make_float4(x, y, z, r);
+	if (mi < nActive) a.tPos[mi] = make_float4(x, y, z, r);
 	uint32_t *sup = a.supList + (size_t)st * a.supCap;
 	int ns = 0;
 	bool overflow = false;
@@ -684,12 +617,13 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, int nSuper
 	if (lane == 0) a.supCnt[st] = overflow ? -1 : ns;
 }
 
-__global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTiles)
+__global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a)
 {
 	const int lane = threadIdx.x & 31;
 	const uint32_t lt = (1u << lane) - 1u;
 	const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
-	if (t >= nTiles) return;
+	const int nActive = N_ACTIVE(a);
+	if (t * TILE >= nActive) return;
 	const float T = __uint_as_float(a.dT[0]);
 	const int st = t / SUPER;
 	const int ns = a.supCnt[st];
@@ -698,7 +632,6 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	if (ns < 0) { // the supertile's members are far apart: own walk (k_tile_walk)
 		if (lane == 0) {
 			a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
-			a.tPend[t] = 1;
 		}
 		return;
 	}
@@ -706,7 +639,7 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	float mxv[TILE], myv[TILE], mzv[TILE];
 #pragma unroll
 	for (int m = 0; m < TILE; ++m) {
-		const uint32_t id = a.act[min(t * TILE + m, a.nActive - 1)]; // a short last tile repeats its last member
+		const uint32_t id = a.act[min(t * TILE + m, nActive - 1)]; // a short last tile repeats its last member
 		mxv[m] = a.mx[id], myv[m] = a.my[id], mzv[m] = a.mz[id];
 	}
 	const float r2 = r * r;
@@ -728,7 +661,6 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 		if (overflow) { // too long for the window's reach: k_tile_walk retries and falls back to a zero-reach list
 			if (lane == 0) {
 				a.tileQueue[atomicAdd(a.tileQueueCount, 1u)] = (uint32_t)t;
-				a.tPend[t] = 1;
 			}
 			return;
 		}
@@ -736,7 +668,6 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a, int nTile
 	if (lane == 0) {
 		a.tCnt[t] = cnt;
 		a.tOff[t] = off;
-		a.tPend[t] = 0;
 	}
 }
 
@@ -759,7 +690,7 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
 	const int cnt = a.tCnt[t];
 	const int mi = t * TILE + m;
-	const bool have = mi < a.nActive;
+	const bool have = mi < N_ACTIVE(a);
 	const uint32_t id = have ? a.act[mi] : 0u;
 	float x = 0.0f, y = 0.0f, z = 0.0f;
 	if (have) x = a.mx[id], y = a.my[id], z = a.mz[id];
@@ -812,25 +743,13 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 	if (run && j == 0) finish_mover(a, id, x, y, z, ax, ay, az, rmin);
 }
 
-// One block per tile.  At a rebuild step the tiles that build their list with their own walk (k_tile_walk, a
-// latency-bound kernel over the few per cent of tiles in dense cores) are still being built on a second
-// stream: the first launch skips them (skip[t] != 0, written by k_tile_filter), a second, queue-driven launch
-// (persistent grid, tiles taken from `queue`) serves them once the walk has finished.
-__global__ void __launch_bounds__(TILE_THREADS)
-    k_tile_step(const StepArgs a, const uint8_t *skip, const uint32_t *queue, const uint32_t *queueCount)
+// One block per tile; the grid is sized from the host's upper bound of the active count.
+__global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
 {
 	__shared__ TileShared sh;
 	__shared__ uint32_t sh_e[TILE_CHUNK];
-	if (queue) {
-		const uint32_t nq = *queueCount;
-		for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
-			if (q != blockIdx.x) __syncthreads(); // the previous tile's staging buffers are still being read
-			tile_step_body(a, (int)queue[q], sh, sh_e);
-		}
-		return;
-	}
 	const int t = blockIdx.x;
-	if (skip && skip[t]) return;
+	if (t * TILE >= N_ACTIVE(a)) return;
 	tile_step_body(a, t, sh, sh_e);
 }
 
@@ -899,128 +818,19 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a,
 	}
 }
 
-// tree-walk refresh of the movers in `queue` (all queued movers without buckets, else those their
-// bucket can not serve)
-__global__ void __launch_bounds__(REFRESH_WARPS * 32) k_list_refresh(const StepArgs a, const uint32_t *queue,
-                                                                     const uint32_t *queueCount)
-{
-	const int lane = threadIdx.x & 31;
-	const uint32_t lt = (1u << lane) - 1u;
-	const uint32_t wi = blockIdx.x * REFRESH_WARPS + (threadIdx.x >> 5);
-	if (wi >= *queueCount) return;
-	const uint32_t id = queue[wi];
-	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
-	const float T = __uint_as_float(a.dT[0]);
-	float ax = 0.0f, ay = 0.0f, az = 0.0f;
-	float rmin = 3.0e38f;
-	uint32_t *list = a.list + (size_t)(id - a.listBase) * LIST_CAP; // lists exist for this shard's movers only
-	const float delta = fminf(fmaxf(a.lhmin[id], 2.0f * a.fStep), 64.0f * a.fStep); // lhmin = margin to use
-	const float delta2 = delta * delta;
-	int nHit = 0;
-	int cnt = 0;
-	bool overflow = false;
-	// one scatterer per lane: hit test for this step, candidate test for the list.
-	// candidate <=> d <= h + delta <=> u = d2 - h^2 - delta^2 <= 2 h delta (no square root; 1e-4 slack)
-#define LIST_PROCESS(e_, p)                                                                            \
-	{                                                                                              \
-		const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);    \
-		const float d2 = dist2_rn(dx, dy, dz);                                                 \
-		const float u = d2 - p.w - delta2;                                                     \
-		bool cand = p.w > 0.0f && (u <= 0.0f || u * u <= 4.0004f * p.w * delta2);              \
-		if (cand) {                                                                            \
-			const float4 q = a.entNR[e_];                                                  \
-			cand = q.z >= T; /* dead scatterers never come back */                         \
-			if (cand && d2 < p.w) {                                                        \
-				ACC_HIT(dx, dy, dz, d2, q);                                            \
-				++nHit;                                                                \
-				if (a.touched) a.touched[e_] = 1;                                      \
-			}                                                                              \
-		}                                                                                      \
-		const uint32_t cm = __ballot_sync(SK_FULL, cand);                                      \
-		const int nc = __popc(cm);                                                             \
-		if (cnt + nc <= LIST_CAP) {                                                            \
-			if (cand) list[cnt + __popc(cm & lt)] = e_;                                    \
-		} else overflow = true;                                                                \
-		cnt += nc;                                                                             \
-	}
-	int lev = a.tv.top - 1;
-	uint32_t node = 0, mymask = 0;
-	const float bx0 = x - delta, bx1 = x + delta, by0 = y - delta, by1 = y + delta, bz0 = z - delta, bz1 = z + delta;
-#define LIST_TEST_CHILDREN()                                                                           \
-	{                                                                                              \
-		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
-		float4 lo = bx[0], hi = bx[1];                                                         \
-		bool in_ = bx1 >= lo.x && bx0 <= hi.x && by1 >= lo.y && by0 <= hi.y && bz1 >= lo.z && bz0 <= hi.z && \
-		           lo.w >= T;                                                                  \
-		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
-		if (lane == lev) mymask = m_;                                                          \
-	}
-	LIST_TEST_CHILDREN();
-	while (true) {
-		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
-		if (m == 0) {
-			++lev;
-			if (lev >= a.tv.top) break;
-			node >>= 5;
-			continue;
-		}
-		int c = __ffs(m) - 1;
-		m &= m - 1;
-		if (lev > 0) {
-			if (lane == lev) mymask = m;
-			uint32_t child = node * 32 + c;
-			--lev;
-			node = child;
-			LIST_TEST_CHILDREN();
-			continue;
-		}
-		// leaf level: take two buckets per round so that two record loads are in flight
-		const uint32_t e0 = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
-		const float4 p0 = a.entPos[e0];
-		if (m) {
-			const int c1 = __ffs(m) - 1;
-			m &= m - 1;
-			const uint32_t e1 = (node * 32 + c1) * 32 + lane;
-			const float4 p1 = a.entPos[e1];
-			if (lane == 0) mymask = m;
-			LIST_PROCESS(e0, p0);
-			LIST_PROCESS(e1, p1);
-		} else {
-			if (lane == 0) mymask = m;
-			LIST_PROCESS(e0, p0);
-		}
-	}
-#undef LIST_TEST_CHILDREN
-#undef LIST_PROCESS
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) nHit += __shfl_xor_sync(SK_FULL, nHit, o);
-	if (lane == 0) {
-		a.lcnt[id] = overflow ? -1 : cnt;
-		a.lx0[id] = x;
-		a.ly0[id] = y;
-		a.lz0[id] = z;
-		a.ldelta[id] = delta;
-		// feedback on the margin: grow it while the list stays short relative to the hits, shrink it
-		// when the list is long (a long list makes every step slower, a short one refreshes often)
-		float next = delta;
-		if (overflow || (float)cnt > a.polShrink * nHit + 32.0f) next = 0.6f * delta;
-		else if ((float)cnt < a.polGrow * nHit + 32.0f && cnt < a.polGrowMax) next = 1.5f * delta;
-		a.lhmin[id] = next;
-	}
-	finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
-}
-
 // After a step: adopt the new threshold (ScatterCut, smooth1.c:509-513).  If nothing was hit the
-// reference's fScatDens stays 0.0 and nothing is cut.
-__global__ void k_update_T(uint32_t *dT, int bNoPrune)
+// reference's fScatDens stays 0.0 and nothing is cut.  Also resets the per-step queues and adds the step's
+// active movers to the stage's mover-step counter.
+__global__ void k_update_T(uint32_t *dT, int bNoPrune, int par, int launched)
 {
-	uint32_t nx = dT[1];
-	if (!bNoPrune && nx != T_NONE) dT[0] = nx;
-	dT[1] = T_NONE;
-	dT[2] = 0u; // refresh queues of the next step: movers, buckets, tree-walk movers
-	dT[3] = 0u;
+	uint32_t nx = dT[DT_MIN];
+	if (!bNoPrune && nx != T_NONE) dT[DT_T] = nx;
+	dT[DT_MIN] = T_NONE;
+	dT[DT_QUEUE] = 0u; // own-walk movers of the next step
+	dT[DT_TILEQ] = 0u;
 	dT[4] = 0u;
-	dT[7] = 0u; // ticket counter of k_tile_walk
+	dT[DT_TICKET] = 0u; // ticket counter of k_tile_walk
+	if (launched) *(unsigned long long *)(dT + DT_STEPS) += dT[DT_NACT + par];
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
@@ -1065,14 +875,19 @@ __global__ void __launch_bounds__(256)
 }
 
 // kdPruneInactive (kd.c:735-793): a mover stays active iff it moved >= fCvg (min image) since the
-// last check.  flags -> scan -> stable compaction of the active list.
+// last check.  flags -> scan -> stable compaction of the active list.  `bound` is the host's upper bound of
+// the device-side count dN[0]; entries beyond the count get flag 0.
 __global__ void __launch_bounds__(256)
-    k_prune_flags(int nActive, const uint32_t *act, const float *mx, const float *my, const float *mz,
+    k_prune_flags(int bound, const uint32_t *dN, const uint32_t *act, const float *mx, const float *my, const float *mz,
                   const float *rox, const float *roy, const float *roz, float hx, float hy, float hz, float fCvg2,
                   uint32_t *flags)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= nActive) return;
+	if (i >= bound) return;
+	if (i >= (int)*dN) {
+		flags[i] = 0u;
+		return;
+	}
 	uint32_t id = act[i];
 	float dx = __fsub_rn(mx[id], rox[id]);
 	float dy = __fsub_rn(my[id], roy[id]);
@@ -1088,13 +903,21 @@ __global__ void __launch_bounds__(256)
 	flags[i] = dr2 >= fCvg2 ? 1u : 0u;
 }
 
+// ... and the new count goes to the other device-side slot and to this block's log slot:
+// log[0] = active movers (summed over the ranks afterwards), log[2] = this rank's own count
 __global__ void __launch_bounds__(256)
-    k_prune_compact(int nActive, const uint32_t *act, const uint32_t *flags, const uint32_t *scan,
+    k_prune_compact(int bound, const uint32_t *act, const uint32_t *flags, const uint32_t *scan,
                     const float *mx, const float *my, const float *mz, float *rox, float *roy, float *roz,
-                    uint32_t *actOut)
+                    uint32_t *actOut, uint32_t *dNnext, uint32_t *log)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= nActive || !flags[i]) return;
+	if (i == 0) {
+		const uint32_t tot = bound > 0 ? scan[bound] : 0u;
+		*dNnext = tot;
+		log[0] = tot;
+		log[2] = tot;
+	}
+	if (i >= bound || !flags[i]) return;
 	uint32_t id = act[i];
 	actOut[scan[i]] = id;
 	rox[id] = mx[id];
@@ -1113,7 +936,7 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.my = c.my.p;
 	sa.mz = c.mz.p;
 	sa.act = c.actList.p;
-	sa.nActive = c.nActive;
+	sa.par = c.actPar;
 	sa.nEnt = c.nEnt;
 	sa.dT = c.dT.p;
 	sa.fStep = fStep;
@@ -1123,31 +946,8 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 		sa.wrapLo[d] = (double)c.C[d] - 0.5 * (double)c.L[d]; // kd.c:726
 	}
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
-	sa.list = c.mList.p;
-	sa.listBase = (uint32_t)c.shardLo;
-	sa.lx0 = c.lx0.p;
-	sa.ly0 = c.ly0.p;
-	sa.lz0 = c.lz0.p;
-	sa.ldelta = c.ldelta.p;
-	sa.lhmin = c.lhmin.p;
-	sa.lcnt = c.lcnt.p;
-	static int wa = -1;
-	if (wa < 0) wa = getenv("SKIDGPU_LIST_WALK_ALWAYS") ? 1 : 0;
-	sa.walkAlways = wa;
-	static float pol[4] = {-1, 0, 0, 0};
-	if (pol[0] < 0) {
-		pol[0] = 3.0f;  // shrink when candidates > 3 x hits (+32)
-		pol[1] = 1.5f;  // grow while candidates < 1.5 x hits (+32)
-		pol[2] = 96.f;  // ... and fewer than this (measured sweep: tools/sweep_policy.sh)
-		pol[3] = 0.3f;  // first margin = 0.3 x own ball radius
-		if (const char *e = getenv("SKIDGPU_LIST_POLICY")) sscanf(e, "%f,%f,%f,%f", &pol[0], &pol[1], &pol[2], &pol[3]);
-	}
-	sa.polShrink = pol[0];
-	sa.polGrow = pol[1];
-	sa.polGrowMax = (int)pol[2];
-	c.listInitFactor = pol[3];
 	sa.queue = c.mQueue.p;
-	sa.queueCount = c.dT.p ? c.dT.p + 2 : nullptr;
+	sa.queueCount = c.dT.p ? c.dT.p + DT_QUEUE : nullptr;
 	for (int d = 0; d < 3; ++d) { // r > t  <=>  r > (largest float <= t) for float r (same for <=)
 		float h = (float)sa.wrapHi[d], l = (float)sa.wrapLo[d];
 		if ((double)h > sa.wrapHi[d]) h = nextafterf(h, -INFINITY);
@@ -1159,189 +959,167 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tOff = c.tOff.p;
 	sa.bigBase = c.bigBase;
 	sa.nBig = c.nBig;
-	sa.bigCount = c.dT.p ? c.dT.p + 6 : nullptr;
+	sa.bigCount = c.dT.p ? c.dT.p + DT_BIG : nullptr;
 	sa.tPos = c.tPos.p;
 	sa.tCnt = c.tCnt.p;
 	sa.supList = c.supList.p;
 	sa.tileQueue = c.tileQueue.p;
-	sa.tileQueueCount = c.dT.p ? c.dT.p + 3 : nullptr;
+	sa.tileQueueCount = c.dT.p ? c.dT.p + DT_TILEQ : nullptr;
 	sa.supCnt = c.supCnt.p;
 	sa.supCap = c.superCap;
-	sa.tPend = c.tPend.p;
-	sa.walkDyn = TILEWALK_DYN_DEFAULT;
-	if (const char *e = getenv("SKIDGPU_TILEWALK_DYN")) sa.walkDyn = atoi(e);
 }
 
-static int count_scatterers(skidgpu_ctx &c)
+// Log slots: one per Ittr block / micro step, 4 words: [0] active movers (all ranks), [1] surviving scatterers
+// (all ranks), [2] this rank's active movers.  Written on the device, copied to pinned host memory behind the
+// block that produced them and read by the host a few blocks later: the loop never waits for the GPU.
+constexpr int LOG_SLOTS = 1024;
+constexpr int LOG_LAG = 2; // blocks enqueued ahead of the last count the host has seen
+
+static uint32_t *log_slot(skidgpu_ctx &c, int b) { return c.dLog.p + 4 * (size_t)(b % LOG_SLOTS); }
+
+static void log_prepare(skidgpu_ctx &c)
 {
-	cudaStream_t s = c.stream;
-	uint32_t *cnt = c.dCount.alloc(4);
-	CK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t), s));
-	// every rank counts its slice of the (replicated) scatterers
+	c.dLog.alloc(4 * LOG_SLOTS);
+	if (!c.hLog) CK(cudaHostAlloc((void **)&c.hLog, sizeof(uint32_t) * 4 * LOG_SLOTS, cudaHostAllocDefault));
+}
+static cudaEvent_t log_event(skidgpu_ctx &c, int b)
+{
+	while ((int)c.logEv.size() <= b % LOG_SLOTS) {
+		cudaEvent_t e;
+		CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		c.logEv.push_back(e);
+	}
+	return c.logEv[b % LOG_SLOTS];
+}
+
+// nScatter of a log line into slot[1]; every rank counts its slice of the (replicated) scatterers
+static void enqueue_count_scatterers(skidgpu_ctx &c, uint32_t *slot)
+{
 	const int lo = (int)((long long)c.nEnt * c.rank / c.nranks), hi = (int)((long long)c.nEnt * (c.rank + 1) / c.nranks);
 	if (hi > lo) {
 		unsigned g = (unsigned)ceil_div(hi - lo, 256 * 8);
-		SK_LAUNCH(k_count_scatter, g > 148u * 8u ? 148u * 8u : g, 256, 0, s, lo, hi, c.entNR.p, c.dT.p, cnt);
+		SK_LAUNCH(k_count_scatter, g > 148u * 8u ? 148u * 8u : g, 256, 0, c.stream, lo, hi, c.entNR.p, c.dT.p, slot + 1);
 	}
-	sk_reduce(c, cnt, 1, SK_I32, SK_SUM);
-	uint32_t h = 0;
-	CK(cudaMemcpyAsync(&h, cnt, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-	CK(cudaStreamSynchronize(s));
-	return (int)h;
 }
-
-// SKIDGPU_MOVE_KERNEL = tile (default) | list (per-mover candidate lists refreshed by tree walks) |
-// warp (v1: a tree walk per mover and step).  The last two are kept for A/B measurements.
-enum { MOVE_TILE = 0, MOVE_LIST = 1, MOVE_WARP = 2 };
-static int move_kernel()
+// close a log slot: sum over the ranks, copy to the pinned mirror, mark with an event
+static void enqueue_log_fetch(skidgpu_ctx &c, int b)
 {
-	static int v = -1;
-	if (v < 0) {
-		const char *e = getenv("SKIDGPU_MOVE_KERNEL");
-		v = MOVE_TILE;
-		if (e && !strcmp(e, "warp")) v = MOVE_WARP;
-		if (e && !strcmp(e, "list")) v = MOVE_LIST;
-	}
-	return v;
+	uint32_t *slot = log_slot(c, b);
+	sk_reduce(c, slot, 2, SK_I32, SK_SUM);
+	CK(cudaMemcpyAsync(c.hLog + 4 * (size_t)(b % LOG_SLOTS), slot, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+	CK(cudaEventRecord(log_event(c, b), c.stream));
+}
+static const uint32_t *wait_log(skidgpu_ctx &c, int b)
+{
+	CK(cudaEventSynchronize(log_event(c, b)));
+	return c.hLog + 4 * (size_t)(b % LOG_SLOTS);
 }
 
-// k_tile_walk is latency bound (dependent tree loads): resident blocks per SM = SKIDGPU_TILEWALK_OCC (4, 6 or 8;
-// the register budget follows from the launch bounds), persistent grid of that many blocks per SM.
+// k_tile_walk is latency bound (dependent tree loads): 8 resident blocks per SM (64 registers via the launch
+// bounds), persistent grid of that many blocks per SM, tiles drawn from a ticket counter.
 static void launch_tile_walk(skidgpu_ctx &c, const StepArgs &sa, const uint32_t *queue, const uint32_t *queueCount,
                              float reach, float reachShort, uint32_t *shortQueue, uint32_t *shortCount)
 {
-	int occ = TILEWALK_OCC_DEFAULT;
-	if (const char *e = getenv("SKIDGPU_TILEWALK_OCC")) occ = atoi(e);
-	if (occ >= 8)
-		SK_LAUNCH(k_tile_walk<8>, 148 * 8, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
-	else if (occ >= 6)
-		SK_LAUNCH(k_tile_walk<6>, 148 * 6, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
-	else if (occ == 5)
-		SK_LAUNCH(k_tile_walk<5>, 148 * 5, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
-	else
-		SK_LAUNCH(k_tile_walk<4>, 148 * 4, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
+	SK_LAUNCH(k_tile_walk<8>, 148 * 8, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
 }
 
 // Sort the active movers by position and build the tile lists; valid for `steps` steps of length fStep.
 static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 {
 	cudaStream_t s = c.stream;
-	c.nTiles = 0;
 	c.tileStepsLeft = steps;
-	if (c.nActive <= 0 || c.nEnt <= 0) return;
+	const int bound = c.nActiveBound;
+	if (bound <= 0 || c.nEnt <= 0) return;
+	c.spans.begin(KF_BUILD, s);
 	// The active list starts in Morton order of the initial positions and compaction keeps its order, so
-	// tiles stay compact for a while: re-sort by current position only every few rebuilds (the lists are
+	// tiles stay compact for a while: re-sort by current position only every 4th rebuild (the lists are
 	// unions of per-member neighbourhoods - compactness is efficiency, never correctness).
-	int every = 4;
-	if (const char *e = getenv("SKIDGPU_TILE_SORT_EVERY")) every = atoi(e);
-	if (every > 0 && c.tileBuilds % every == every - 1) {
-		uint64_t *keys = c.tKeys.alloc(c.nActive);
-		SK_LAUNCH(k_mover_keys, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
+	if (c.tileBuilds % 4 == 3) {
+		uint64_t *keys = c.tKeys.alloc(bound);
+		SK_LAUNCH(k_mover_keys, (unsigned)ceil_div(bound, 256), 256, 0, s, bound, c.dT.p + DT_NACT + c.actPar, c.actList.p, c.mx.p,
 		          c.my.p, c.mz.p, c.treeM.bbox.p, keys, c.actList2.p);
-		radix_sort_pairs(keys, c.actList2.p, c.nActive, 63, c.ws, s);
+		radix_sort_pairs(keys, c.actList2.p, bound, 63, c.ws, s); // entries beyond the device-side count sort to the end
 		std::swap(c.actList.p, c.actList2.p);
 		std::swap(c.actList.cap, c.actList2.cap);
 	}
 	++c.tileBuilds;
-	c.nTiles = (int)ceil_div(c.nActive, TILE);
 	sa.act = c.actList.p;
-	sa.nActive = c.nActive;
-	const int nSuper = (int)ceil_div(c.nTiles, SUPER);
-	CK(cudaMemsetAsync(c.dT.p + 5, 0, 2 * sizeof(uint32_t), s)); // short-tile queue, big slots in use
+	sa.par = c.actPar;
+	const int nTiles = (int)ceil_div(bound, TILE), nSuper = (int)ceil_div(nTiles, SUPER);
+	CK(cudaMemsetAsync(c.dT.p + DT_SHORTQ, 0, 2 * sizeof(uint32_t), s)); // short-tile queue, big slots in use
 	// a list built now is evaluated at the current positions and after 1 .. steps-1 moves of length fStep
 	const float reach = (float)(steps - 1) * sa.fStep;
-	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, nSuper, reach);
-	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(c.nTiles, 4), 128, 0, s, sa, c.nTiles);
-	// spread-out supertiles build per tile; tiles whose 5-step list overflows become short tiles (dT[5])
-	c.tileOverlap = TILE_OVERLAP_DEFAULT;
-	if (const char *e = getenv("SKIDGPU_TILE_OVERLAP")) c.tileOverlap = atoi(e);
-	if (c.tileOverlap) { // the walk of the queued tiles runs beside the step of all the others (one_step)
-		CK(cudaEventRecord(c.evWalk0, s));
-		CK(cudaStreamWaitEvent(c.stream2, c.evWalk0, 0));
-		std::swap(c.stream, c.stream2);
-		launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
-		std::swap(c.stream, c.stream2);
-		CK(cudaEventRecord(c.evWalk1, c.stream2));
-	} else
-		launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + 5);
+	SK_LAUNCH(k_super_walk, (unsigned)ceil_div(nSuper, 4), 128, 0, s, sa, reach);
+	SK_LAUNCH(k_tile_filter, (unsigned)ceil_div(nTiles, 4), 128, 0, s, sa);
+	// spread-out supertiles build per tile; tiles whose 5-step list overflows become short tiles (DT_SHORTQ)
+	launch_tile_walk(c, sa, sa.tileQueue, sa.tileQueueCount, reach, steps > 1 ? 0.0f : -1.0f, c.shortQueue.p, c.dT.p + DT_SHORTQ);
+	c.spans.end(s);
 	c.tileFresh = true;
-	if (getenv("SKIDGPU_TILE_DIAG")) {
-		std::vector<int> h(c.nTiles);
-		CK(cudaMemcpyAsync(h.data(), c.tCnt.p, sizeof(int) * c.nTiles, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-		long long sum = 0;
-		int over = 0, hist[16] = {0};
-		for (int v : h) {
-			if (v < 0) {
-				++over;
-				continue;
-			}
-			sum += v;
-			int b = v / 128;
-			++hist[b > 15 ? 15 : b];
-		}
-		fprintf(stderr, "tiles: n=%d active=%d steps=%d overflow=%d mean=%.1f hist128:", c.nTiles, c.nActive, steps, over,
-		        c.nTiles > over ? (double)sum / (c.nTiles - over) : 0.0);
-		for (int b = 0; b < 16; ++b) fprintf(stderr, " %d", hist[b]);
-		fprintf(stderr, "\n");
-		std::vector<int> hs(nSuper);
-		CK(cudaMemcpyAsync(hs.data(), c.supCnt.p, sizeof(int) * nSuper, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-		long long ssum = 0;
-		int sover = 0;
-		for (int v : hs) {
-			if (v < 0) ++sover;
-			else ssum += v;
-		}
-		uint32_t hq[8];
-		CK(cudaMemcpyAsync(hq, c.dT.p, sizeof hq, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-		fprintf(stderr, "supertiles: n=%d overflow=%d mean=%.1f cap=%d | walked tiles=%u short tiles=%u big slots=%u/%u\n", nSuper,
-		        sover, nSuper > sover ? (double)ssum / (nSuper - sover) : 0.0, c.superCap, hq[3], hq[5], hq[6], c.nBig);
-	}
 }
 
-static int one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
+// One step of smAccDensity + kdMoveParticles for every active mover (everything is enqueued; nothing waits).
+static void one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 {
+	cudaStream_t s = c.stream;
+	const int bound = c.nActiveBound;
 	int launched = 0;
-	if (c.nActive > 0 && c.nEnt > 0) {
+	if (bound > 0 && c.nEnt > 0) {
 		launched = 1;
 		sa.act = c.actList.p;
-		sa.nActive = c.nActive;
-		const int mk = move_kernel();
-		if (mk == MOVE_TILE) {
+		sa.par = c.actPar;
+		if (c.moveKernel == 0) {
 			if (c.tileStepsLeft <= 0) rebuild_tiles(c, sa, c.tileWindow);
 			--c.tileStepsLeft;
-			if (!c.tileFresh) // short tiles are rebuilt before every step (their list has no reach)
-				launch_tile_walk(c, sa, c.shortQueue.p, c.dT.p + 5, -1.0f, 0.0f, nullptr, nullptr);
-			const bool overlapped = c.tileFresh && c.tileOverlap;
+			if (!c.tileFresh) { // short tiles are rebuilt before every step (their list has no reach)
+				c.spans.begin(KF_FALLBACK, s);
+				launch_tile_walk(c, sa, c.shortQueue.p, c.dT.p + DT_SHORTQ, -1.0f, 0.0f, nullptr, nullptr);
+				c.spans.end(s);
+			}
 			c.tileFresh = false;
-			if (overlapped) {
-				SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa, sa.tPend, (const uint32_t *)nullptr,
-				          (const uint32_t *)nullptr);
-				CK(cudaStreamWaitEvent(c.stream, c.evWalk1, 0));
-				SK_LAUNCH(k_tile_step, 148 * 16, TILE_THREADS, 0, c.stream, sa, (const uint8_t *)nullptr, sa.tileQueue,
-				          sa.tileQueueCount);
-			} else
-				SK_LAUNCH(k_tile_step, (unsigned)c.nTiles, TILE_THREADS, 0, c.stream, sa, (const uint8_t *)nullptr,
-				          (const uint32_t *)nullptr, (const uint32_t *)nullptr);
-			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, c.stream, sa, sa.queue, 0, sa.queueCount);
-		} else if (mk == MOVE_LIST) {
-			SK_LAUNCH(k_list_eval, (unsigned)ceil_div(c.nActive, EVAL_WARPS), EVAL_WARPS * 32, 0, c.stream, sa);
-			// grid sized for the worst case (everybody refreshes); warps beyond the queue length exit at once
-			SK_LAUNCH(k_list_refresh, (unsigned)ceil_div(c.nActive, REFRESH_WARPS), REFRESH_WARPS * 32, 0, c.stream,
-			          sa, sa.queue, sa.queueCount);
-		} else {
-			unsigned g = (unsigned)ceil_div(c.nActive, STEP_WARPS);
-			SK_LAUNCH(k_move_step, g > 148u * 64u ? 148u * 64u : g, STEP_WARPS * 32, 0, c.stream, sa, sa.act,
-			          c.nActive, (const uint32_t *)nullptr);
+			c.spans.begin(KF_TILE_STEP, s);
+			SK_LAUNCH(k_tile_step, (unsigned)ceil_div(bound, TILE), TILE_THREADS, 0, s, sa);
+			c.spans.end(s);
+			c.spans.begin(KF_FALLBACK, s);
+			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, s, sa, sa.queue, 0, sa.queueCount);
+			c.spans.end(s);
+		} else { // test hook: a tree walk per mover and step (the v1 kernel)
+			unsigned g = (unsigned)ceil_div(bound, STEP_WARPS);
+			SK_LAUNCH(k_move_step, g > 148u * 64u ? 148u * 64u : g, STEP_WARPS * 32, 0, s, sa, sa.act, 0,
+			          (const uint32_t *)(c.dT.p + DT_NACT + c.actPar));
 		}
-		c.moverSteps += c.nActive;
 	}
-	if (!bNoPrune) sk_reduce(c, c.dT.p + 1, 1, SK_I32, SK_MIN); // fScatDens over all ranks' movers (+inf bits = none)
-	SK_LAUNCH(k_update_T, 1, 1, 0, c.stream, c.dT.p, bNoPrune);
-	return launched;
+	if (!bNoPrune) sk_reduce(c, c.dT.p + DT_MIN, 1, SK_I32, SK_MIN); // fScatDens over all ranks' movers (+inf bits = none)
+	SK_LAUNCH(k_update_T, 1, 1, 0, s, c.dT.p, bNoPrune, c.actPar, launched);
 }
+
+// kdPruneInactive + the counts of one "Ittr" line into log slot b
+static void enqueue_prune(skidgpu_ctx &c, int b, float hx, float hy, float hz, float fCvg2)
+{
+	cudaStream_t s = c.stream;
+	const int bound = c.nActiveBound;
+	uint32_t *slot = log_slot(c, b);
+	c.spans.begin(KF_PRUNE, s);
+	CK(cudaMemsetAsync(slot, 0, 4 * sizeof(uint32_t), s));
+	uint32_t *pf = c.flags.alloc((size_t)bound + 1);
+	uint32_t *ps = c.scan.alloc((size_t)bound + 64);
+	uint32_t *dN = c.dT.p + DT_NACT;
+	if (bound > 0) {
+		SK_LAUNCH(k_prune_flags, (unsigned)ceil_div(bound, 256), 256, 0, s, bound, dN + c.actPar, c.actList.p, c.mx.p, c.my.p,
+		          c.mz.p, c.rox.p, c.roy.p, c.roz.p, hx, hy, hz, fCvg2, pf);
+		exclusive_scan_u32(pf, ps, bound, c.ws, s);
+	}
+	SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(bound > 0 ? bound : 1, 256), 256, 0, s, bound, c.actList.p, pf, ps, c.mx.p,
+	          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p, dN + (c.actPar ^ 1), slot);
+	enqueue_count_scatterers(c, slot);
+	c.spans.end(s);
+	enqueue_log_fetch(c, b);
+	c.actPar ^= 1;
+	std::swap(c.actList.p, c.actList2.p);
+	std::swap(c.actList.cap, c.actList2.cap);
+	c.tileStepsLeft = 0; // the active list changed: new tiles
+}
+
+static void resolve_spans(skidgpu_ctx &c) { c.spans.resolve(c.kernel_ms, c.kernel_launches); }
 
 void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,
                 int bForceInitialCut, int bNoPrune, skidgpu_log_cb cb, void *user, int *nMoveOut, int *nIttrOut)
@@ -1352,9 +1130,9 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	if (!c.rho.p) throw SkidError("skidgpu_move: skidgpu_density has not run");
 	StageTimer tm(c, 1);
 	c.bNoPrune = bNoPrune;
-	{
-		StepArgs tmp;
-		fill_step_args(c, tmp, fStep); // also reads the list policy (listInitFactor) from the environment
+	for (int f : {KF_TILE_STEP, KF_BUILD, KF_FALLBACK, KF_PRUNE}) {
+		c.kernel_ms[f] = 0;
+		c.kernel_launches[f] = 0;
 	}
 
 	// ---- kdInitMove
@@ -1369,23 +1147,20 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.nMove = (int)nm;
 	c.haveCenters = false;
 	const int m = c.nMove;
-	uint32_t *dT = c.dT.alloc(8);
-	uint32_t initT[8] = {0u, T_NONE, 0u, 0u, 0u, 0u, 0u, 0u}; // threshold, running min of this step, queue lengths, ticket
+	uint32_t *dT = c.dT.alloc(DT_WORDS);
+	uint32_t initT[DT_WORDS] = {0u, T_NONE}; // threshold, running min of this step, queue lengths, ticket, counts
 	CK(cudaMemcpyAsync(dT, initT, sizeof initT, cudaMemcpyHostToDevice, s));
+	log_prepare(c);
+	c.actPar = 0;
 	c.shardLo = (int)((long long)m * c.rank / c.nranks);
 	c.shardHi = (int)((long long)m * (c.rank + 1) / c.nranks);
-	c.nActive = c.shardHi - c.shardLo;
-	// block-cyclic ownership on several GPUs (the per-mover lists of SKIDGPU_MOVE_KERNEL=list are indexed
-	// by id - shardLo and keep the contiguous range)
-	c.cyclic = c.nranks > 1 && move_kernel() != MOVE_LIST;
-	if (c.cyclic) c.nActive = owned_count(m, c.rank, c.nranks);
-	c.nOwned = c.nActive;
+	c.nOwned = c.nranks > 1 ? owned_count(m, c.rank, c.nranks) : m; // block-cyclic ownership on several GPUs
 	if (m > 0) {
 		uint32_t *fileIdx = c.actList2.alloc(m);
 		SK_LAUNCH(k_compact_idx2, (unsigned)ceil_div(n, 256), 256, 0, s, n, flags, scan, fileIdx);
 		float *gx = c.tmpx.alloc(m), *gy = c.tmpy.alloc(m), *gz = c.tmpz.alloc(m);
 		SK_LAUNCH(k_gather3b, (unsigned)ceil_div(m, 256), 256, 0, s, m, fileIdx, c.x.p, c.y.p, c.z.p, gx, gy, gz);
-		tree_sort_points(c.treeM, gx, gy, gz, m, c.ws, s);
+		tree_sort_points(c.treeM, gx, gy, gz, m, c.ws, s, nullptr, &c);
 		c.mx.alloc(m);
 		c.my.alloc(m);
 		c.mz.alloc(m);
@@ -1393,30 +1168,21 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.roy.alloc(m);
 		c.roz.alloc(m);
 		c.mOrd.alloc(m);
-		c.lx0.alloc(m);
-		c.ly0.alloc(m);
-		c.lz0.alloc(m);
-		c.ldelta.alloc(m);
-		c.lhmin.alloc(m);
-		c.lcnt.alloc(m);
 		const int own = c.nOwned;
-		if (move_kernel() == MOVE_LIST) c.mList.alloc((size_t)(own > 0 ? own : 1) * LIST_CAP);
 		c.mQueue.alloc(own > 0 ? own : 1);
-		if (move_kernel() == MOVE_TILE) {
+		{
 			const size_t nt = ceil_div(own > 0 ? own : 1, TILE);
 			// list offsets are 32-bit: 8.3 M tiles (67 M movers on ONE GPU) would overflow them - fail loudly
 			if (nt * TILE_CAP + (nt / 8 + 1024) * (size_t)BIG_CAP >= (1ull << 32))
 				throw SkidError("skidgpu_move: too many movers on one GPU for the 32-bit tile-list offsets; shard the "
-				                "movers over more GPUs (skidgpu_set_shard)");
+				                "movers over more GPUs (skidgpu_comm_init)");
 			c.bigBase = (uint32_t)(nt * TILE_CAP);
 			c.nBig = (uint32_t)(nt / 8 + 1024);
 			c.tList.alloc(nt * TILE_CAP + (size_t)c.nBig * BIG_CAP);
 			c.tOff.alloc(nt);
 			c.tPos.alloc(nt * TILE);
 			c.tCnt.alloc(nt);
-			c.tPend.alloc(nt);
 			c.superCap = SUPER_CAP;
-			if (const char *e = getenv("SKIDGPU_SUPER_CAP")) c.superCap = std::max(256, atoi(e)) & ~31;
 			c.supList.alloc(ceil_div(nt, SUPER) * (size_t)c.superCap);
 			c.supCnt.alloc(ceil_div(nt, SUPER));
 			c.tileQueue.alloc(nt);
@@ -1425,11 +1191,11 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.tileStepsLeft = 0;
 		c.tileBuilds = 0;
 		SK_LAUNCH(k_init_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, c.treeM.perm.p, fileIdx, c.x.p, c.y.p,
-		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p, c.ball2.p, c.lhmin.p, c.lcnt.p, c.listInitFactor);
+		          c.z.p, c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.mOrd.p);
 		c.actList.alloc(m);
 		c.actList2.alloc(m); // fileIdx no longer needed after k_init_movers (same stream)
-		init_active_list(c);
 	}
+	init_active_list(c);
 	if (nMoveOut) *nMoveOut = m;
 
 	// ---- step 0 (main.c:396-404)
@@ -1448,18 +1214,14 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		CK(cudaMemsetAsync(c.entTouched.p, 0, c.nEnt, s));
 		sa.touched = c.entTouched.p;
 	}
-	int nActiveLog = c.nActive;
-	KernelTimer kt(c, 0);
-	c.kernel_ms[0] = 0;
-	c.kernel_launches[0] = 0;
-	kt.start();
 	c.tileWindow = 1; // step 0 is followed by the initial cut and the log line; the blocks of 5 start after it
-	kt.stop(one_step(c, sa, bNoPrune));
+	one_step(c, sa, bNoPrune);
 	c.tileStepsLeft = 0;
 	c.tileWindow = 5;
-	if (bInitial && c.nEnt > 0) sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
-	if (bInitial && c.nEnt > 0)
+	if (bInitial && c.nEnt > 0) {
+		sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
 		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p);
+	}
 	sa.touched = nullptr;
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
 	if (c.keepStep0 && c.nEnt > 0) {
@@ -1467,74 +1229,87 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		SK_LAUNCH(k_alive_by_order, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entNR.p, c.entSrc.p,
 		          c.iordA.p, c.dT.p, c.aliveByOrd.p);
 	}
-	int nScat = count_scatterers(c);
-	if (cb) cb(user, 0, 0, c.nranks > 1 ? m : nActiveLog, nScat);
+	{ // "Ittr:0" line: all movers active
+		uint32_t *slot = log_slot(c, 0);
+		CK(cudaMemsetAsync(slot, 0, 4 * sizeof(uint32_t), s));
+		enqueue_count_scatterers(c, slot);
+		enqueue_log_fetch(c, 0);
+	}
 
-	// ---- main flow loop (main.c:408-419)
+	// ---- main flow loop (main.c:408-419).  The host runs LOG_LAG blocks ahead of the counts it has seen: the
+	// active count lives on the device, grids are sized from the last count the host knows (counts only fall),
+	// and the blocks enqueued after the last mover froze find nothing to do.  All ranks see the same summed
+	// count, hence take the same decisions.
 	const float hx = (float)(0.5 * (double)c.L[0]), hy = (float)(0.5 * (double)c.L[1]),
 	            hz = (float)(0.5 * (double)c.L[2]);
 	const float fCvg2 = fCvg * fCvg;
-	int nIttr = 1;
-	// all ranks iterate until NO rank has an active mover (the per-step fScatDens is a global minimum)
-	auto global_active = [&](int local) -> long long {
-		if (c.nranks <= 1) return local;
-		uint32_t *d = c.dCount.alloc(4);
-		uint32_t h = (uint32_t)local;
-		CK(cudaMemcpyAsync(d + 1, &h, sizeof h, cudaMemcpyHostToDevice, s));
-		sk_reduce(c, d + 1, 1, SK_I32, SK_SUM);
-		CK(cudaMemcpyAsync(&h, d + 1, sizeof h, cudaMemcpyDeviceToHost, s));
-		CK(cudaStreamSynchronize(s));
-		return (long long)h;
-	};
-	long long nGlobal = global_active(c.nActive);
-	while (nGlobal) {
-		int nl = 0;
-		kt.start();
-		const double ms0 = c.kernel_ms[0];
-		const int na0 = c.nActive;
-		for (int i = 0; i < 5; ++i) nl += one_step(c, sa, bNoPrune);
-		kt.stop(nl);
-		if (getenv("SKIDGPU_STEP_TRACE") && c.rank == 0)
-			fprintf(stderr, "ittr %d nActive %d ms5 %.3f\n", nIttr, na0, c.kernel_ms[0] - ms0);
-		// kdPruneInactive
-		uint32_t na = 0;
-		if (c.nActive > 0) {
-			uint32_t *pf = c.flags.alloc(c.nActive);
-			uint32_t *ps = c.scan.alloc((size_t)c.nActive + 64);
-			SK_LAUNCH(k_prune_flags, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, c.mx.p,
-			          c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, hx, hy, hz, fCvg2, pf);
-			exclusive_scan_u32(pf, ps, c.nActive, c.ws, s);
-			SK_LAUNCH(k_prune_compact, (unsigned)ceil_div(c.nActive, 256), 256, 0, s, c.nActive, c.actList.p, pf, ps,
-			          c.mx.p, c.my.p, c.mz.p, c.rox.p, c.roy.p, c.roz.p, c.actList2.p);
-			CK(cudaMemcpyAsync(&na, ps + c.nActive, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-		}
-		nScat = count_scatterers(c); // synchronises
-		c.nActive = (int)na;
-		std::swap(c.actList.p, c.actList2.p);
-		std::swap(c.actList.cap, c.actList2.cap);
-		c.tileStepsLeft = 0; // the active list changed: new tiles
-		nGlobal = global_active(c.nActive);
-		if (cb) cb(user, 0, nIttr, (int)nGlobal, nScat);
-		++nIttr;
+	int nIttr = 1;      // log lines delivered
+	int enq = 1;        // log slots enqueued (slot 0 = step 0)
+	bool done = m == 0; // main.c:408: while (nActive)
+	{
+		const uint32_t *l0 = wait_log(c, 0);
+		if (cb) cb(user, 0, 0, m, (int)l0[1]);
 	}
+	while (!done) {
+		for (int i = 0; i < 5; ++i) one_step(c, sa, bNoPrune);
+		enqueue_prune(c, enq, hx, hy, hz, fCvg2);
+		++enq;
+		// read the counts that are LOG_LAG blocks old (all ranks must enqueue the same blocks, so only a single
+		// GPU may also take counts that happen to be ready earlier)
+		while (nIttr < enq &&
+		       (enq - nIttr > LOG_LAG || (c.nranks == 1 && cudaEventQuery(log_event(c, nIttr)) == cudaSuccess))) {
+			const uint32_t *l = wait_log(c, nIttr);
+			c.nActiveBound = (int)l[2];
+			if (cb) cb(user, 0, nIttr, (int)l[0], (int)l[1]);
+			++nIttr;
+			if (l[0] == 0u) {
+				done = true;
+				break;
+			}
+		}
+	}
+	// blocks enqueued past the end moved nothing; wait for them and for the counters
+	unsigned long long steps = 0;
+	CK(cudaMemcpyAsync(&steps, c.dT.p + DT_STEPS, sizeof steps, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	c.moverSteps += (long long)steps;
+	c.nActive = 0;
+	c.nActiveBound = 0;
+	exchange_positions(c);
 	if (nIttrOut) *nIttrOut = nIttr;
 	tm.stop();
+	resolve_spans(c);
 }
 
 void stage_microstep(skidgpu_ctx &c, int nSteps, float fStep, skidgpu_log_cb cb, void *user)
 {
 	cudaStream_t s = c.stream;
 	StageTimer tm(c, 3);
+	if (!c.dT.p) throw SkidError("skidgpu_microstep: skidgpu_move has not run");
+	if (nSteps > LOG_SLOTS) throw SkidError("skidgpu_microstep: too many steps");
 	// kdReactivateMove (kd.c:796-799)
-	c.nActive = c.nOwned;
 	init_active_list(c);
+	CK(cudaMemsetAsync(c.dT.p + DT_STEPS, 0, 2 * sizeof(uint32_t), s));
 	c.tileStepsLeft = 0;
 	c.tileWindow = nSteps > 0 ? nSteps : 1;
 	StepArgs sa;
 	fill_step_args(c, sa, fStep);
 	for (int i = 0; i < nSteps; ++i) {
 		one_step(c, sa, c.bNoPrune); // smAccDensity keeps cutting scatterers during the micro steps
-		if (cb) cb(user, 1, i + 1, c.nActive, count_scatterers(c));
+		uint32_t *slot = log_slot(c, i);
+		CK(cudaMemsetAsync(slot, 0, 4 * sizeof(uint32_t), s));
+		enqueue_count_scatterers(c, slot);
+		enqueue_log_fetch(c, i);
 	}
+	for (int i = 0; i < nSteps; ++i) {
+		const uint32_t *l = wait_log(c, i);
+		if (cb) cb(user, 1, i + 1, c.nOwned, (int)l[1]);
+	}
+	unsigned long long steps = 0;
+	CK(cudaMemcpyAsync(&steps, c.dT.p + DT_STEPS, sizeof steps, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	c.moverSteps += (long long)steps;
+	exchange_positions(c);
 	tm.stop();
+	resolve_spans(c);
 }

@@ -1,7 +1,7 @@
 // Device-wide exclusive scan and stable LSD radix sort (hand-written; no CUB/thrust).
 #include "common.cuh"
 
-long long g_skid_launches = 0;
+thread_local long long g_skid_launches = 0;
 
 // ------------------------------------------------------------------ scan
 constexpr int SC_THREADS = 256;

@@ -4,7 +4,7 @@
 // the GPU index is designed for warp-wide traversal instead: points are sorted by 63-bit Morton
 // key, cut into buckets of 32 consecutive points (one coalesced 512 B float4 load per bucket),
 // and every internal node has 32 children so a warp tests all child boxes of a node at once.
-#include "common.cuh"
+#include "ctx.cuh"
 
 __device__ __forceinline__ uint64_t spread21(uint32_t v)
 {
@@ -105,8 +105,91 @@ void tree_bbox_only(BoxTree &t, const float *x, const float *y, const float *z, 
 	SK_LAUNCH(k_bbox_finish, 1, 32, 0, s, bbox);
 }
 
+// ------------------------------------------------------------------ distributed sort
+// Every rank holds the same n (key, val) pairs (the snapshot is replicated), so the splitters need
+// no communication: a regular sample of the keys is sorted by everybody, rank r keeps the pairs whose key
+// lies in [split[r], split[r+1]) - in input order, so the stable local sort leaves equal keys in input
+// order exactly like one global stable sort - sorts them and the pieces are all-gathered in rank order.
+constexpr int DS_SAMPLES = 1 << 16;
+
+__global__ void __launch_bounds__(256) k_ds_sample(const uint64_t *keys, size_t n, size_t stride, int ns, uint64_t *samp, uint32_t *sv)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= ns) return;
+	samp[i] = keys[(size_t)i * stride];
+	sv[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256)
+    k_ds_flags(const uint64_t *keys, size_t n, const uint64_t *samp, int ns, int rank, int nranks, uint32_t *flags)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint64_t lo = rank == 0 ? 0ull : samp[(size_t)ns * rank / nranks];
+	const uint64_t k = keys[i];
+	bool in = k >= lo;
+	if (rank < nranks - 1) in = in && k < samp[(size_t)ns * (rank + 1) / nranks];
+	flags[i] = in ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+    k_ds_compact(const uint64_t *keys, const uint32_t *vals, size_t n, const uint32_t *flags, const uint32_t *scan, uint64_t *ko,
+                 uint32_t *vo, int *cnt, int rank)
+{
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0) cnt[rank] = (int)scan[n];
+	if (i >= n || !flags[i]) return;
+	ko[scan[i]] = keys[i];
+	vo[scan[i]] = vals[i];
+}
+
+void dist_sort_pairs(skidgpu_ctx &c, uint64_t *keys, uint32_t *vals, size_t n, int bits)
+{
+	cudaStream_t s = c.stream;
+	Workspace &ws = c.ws;
+	if (c.nranks <= 1 || !c.comm || n < (size_t)DS_SAMPLES * 4) { // small inputs: everybody sorts everything
+		radix_sort_pairs(keys, vals, n, bits, ws, s);
+		return;
+	}
+	const int ns = DS_SAMPLES;
+	uint64_t *samp = ws.dsSamp.alloc(ns);
+	uint32_t *sv = ws.dsSampV.alloc(ns);
+	SK_LAUNCH(k_ds_sample, (unsigned)ceil_div(ns, 256), 256, 0, s, keys, n, n / ns, ns, samp, sv);
+	radix_sort_pairs(samp, sv, ns, bits, ws, s);
+	uint32_t *flags = ws.dsFlag.alloc(n), *scan = ws.dsScan.alloc(n + 64);
+	SK_LAUNCH(k_ds_flags, (unsigned)ceil_div(n, 256), 256, 0, s, keys, n, samp, ns, c.rank, c.nranks, flags);
+	exclusive_scan_u32(flags, scan, n, ws, s);
+	// an upper bound of this rank's share without a round trip: the sample puts ~n/nranks in every range;
+	// the buffers are sized for twice that and the exact counts are checked below
+	const size_t cap = 2 * (n / c.nranks) + 4096;
+	uint64_t *ko = ws.dsKey.alloc(cap);
+	uint32_t *vo = ws.dsVal.alloc(cap);
+	int *cnt = ws.dsCnt.alloc(c.nranks + 1);
+	uint32_t mine = 0;
+	CK(cudaMemcpyAsync(&mine, scan + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	if (mine > cap) { // pathological key distribution (many equal keys): grow
+		ko = ws.dsKey.alloc(mine);
+		vo = ws.dsVal.alloc(mine);
+	}
+	SK_LAUNCH(k_ds_compact, (unsigned)ceil_div(n, 256), 256, 0, s, keys, vals, n, flags, scan, ko, vo, cnt, c.rank);
+	radix_sort_pairs(ko, vo, mine, bits, ws, s);
+	sk_allgather(c, cnt, 1, SK_I32);
+	std::vector<int> hc(c.nranks);
+	CK(cudaMemcpyAsync(hc.data(), cnt, sizeof(int) * c.nranks, cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	std::vector<long long> counts(c.nranks), offs(c.nranks);
+	long long tot = 0;
+	for (int r = 0; r < c.nranks; ++r) {
+		counts[r] = hc[r];
+		offs[r] = tot;
+		tot += hc[r];
+	}
+	if (tot != (long long)n) throw SkidError("dist_sort_pairs: the ranks do not hold the same input (piece sizes do not add up)");
+	sk_allgatherv(c, vo, vals, counts.data(), offs.data(), SK_I32);
+	// only the order travels: no caller reads the sorted keys (keys[] is left unsorted on several ranks)
+}
+
 void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z, int n, Workspace &ws,
-                      cudaStream_t s, const float *radius)
+                      cudaStream_t s, const float *radius, skidgpu_ctx *dist)
 {
 	t.n = n;
 	float *bbox = t.bbox.alloc(8);
@@ -115,7 +198,8 @@ void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z
 	if (n == 0) return;
 	tree_bbox_only(t, x, y, z, n, s);
 	SK_LAUNCH(k_morton, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, radius, keys, perm);
-	radix_sort_pairs(keys, perm, n, 63, ws, s);
+	if (dist) dist_sort_pairs(*dist, keys, perm, n, 63);
+	else radix_sort_pairs(keys, perm, n, 63, ws, s);
 }
 
 // Leaf boxes: `leaf` consecutive sorted points per leaf (leaf = 8, 16 or 32 lanes of a warp).

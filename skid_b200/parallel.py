@@ -1,14 +1,17 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the few exchange
-points of the sharded pipeline.  The library calls back into `Reducer` at its agreement
-points (include/skidgpu.h: skidgpu_reduce_cb); the all-gather of converged mover positions before
-FoF / centres is driven from here.
+"""Multi-GPU plumbing for tests and bench.py: one process per GPU (torchrun).  The exchanges of the sharded
+pipeline are issued by the LIBRARY with NCCL over NVLink on its own stream (csrc/dist.cu);
+torch.distributed only carries the 128-byte NCCL id to the ranks (`init_comm`) and, in bench.py, the synthetic
+snapshot.  host/skid -gpus N does the same from C with one host thread per GPU.
 
-What is sharded: kNN queries (contiguous Morton ranges; fBall2 and f64 density partials are summed),
-movers (block-cyclic over the Morton-ordered mover list: contiguous ranges leave whole halos on one
-rank and the others wait for it at every step) and groups for unbinding (g % nranks).
-What is replicated: particles, trees, scatterers, FoF, catalogue bookkeeping.
+What is shared between the ranks: the sorts behind the tree builds (every rank sorts one key range of the
+replicated input, the pieces are all-gathered), kNN queries (contiguous Morton ranges; fBall2 all-gathered, f64
+density partials summed), movers (block-cyclic over the Morton-ordered mover list: contiguous ranges leave whole
+halos on one rank and the others wait for it at every step) and groups for unbinding (g % nranks).
+What is replicated: particles, tree boxes, scatterers, FoF, catalogue bookkeeping.
 
-The same code runs on CPU with the gloo backend on host buffers (tests/test_parallel_cpu.py).
+`Reducer` is the callback shim (skidgpu_set_reduce_cb) kept for tests; with the gloo backend on host buffers it
+runs on CPU (tests/test_parallel_cpu.py), as do the numpy mirrors of the library's ownership and distributed-sort
+layouts below.
 """
 import ctypes as C
 
@@ -25,6 +28,58 @@ def shard_range(n, rank, nranks):
     """Contiguous range [lo, hi) of n items owned by `rank` (same rule as the library: kd shards are
     floor(n*rank/nranks) .. floor(n*(rank+1)/nranks))."""
     return (n * rank) // nranks, (n * (rank + 1)) // nranks
+
+
+OWN_BLOCK = 4096  # csrc/move.cu: movers are owned in blocks of this many consecutive (Morton-ordered) movers
+
+
+def owned_ids(m, rank, nranks):
+    """Mirror of k_owned_ids / owned_count (csrc/move.cu): mover ids owned by `rank`, block-cyclic."""
+    ids = np.arange(m, dtype=np.int64)
+    return ids[(ids // OWN_BLOCK) % nranks == rank]
+
+
+def pack_owned(x, rank, nranks):
+    """Mirror of k_pack_owned: this rank's slot of the position exchange buffer (one plane)."""
+    m = len(x)
+    nb = -(-m // OWN_BLOCK)
+    per_blocks = -(-nb // nranks)
+    slot = np.zeros(per_blocks * OWN_BLOCK, x.dtype)
+    ids = owned_ids(m, rank, nranks)
+    lb = (ids // OWN_BLOCK) // nranks
+    slot[lb * OWN_BLOCK + ids % OWN_BLOCK] = x[ids]
+    return slot
+
+
+def unpack_all(slots, m, nranks):
+    """Mirror of k_unpack_all: mover array from the all-gathered slots (slots[r] = rank r's plane)."""
+    ids = np.arange(m, dtype=np.int64)
+    blk = ids // OWN_BLOCK
+    r = blk % nranks
+    return np.stack(slots)[r, (blk // nranks) * OWN_BLOCK + ids % OWN_BLOCK]
+
+
+def dist_sort_piece(keys, rank, nranks, samples=1 << 16):
+    """Mirror of dist_sort_pairs (csrc/tree.cu): the (stable) sorted piece of the permutation that `rank`
+    contributes; the concatenation over ranks equals one global stable sort."""
+    n = len(keys)
+    if nranks == 1 or n < 4 * samples:
+        return np.argsort(keys, kind="stable") if rank == 0 else np.zeros(0, np.int64)
+    samp = np.sort(keys[np.arange(samples) * (n // samples)], kind="stable")
+    lo = 0 if rank == 0 else samp[samples * rank // nranks]
+    sel = keys >= lo
+    if rank < nranks - 1:
+        sel &= keys < samp[samples * (rank + 1) // nranks]
+    idx = np.nonzero(sel)[0]
+    return idx[np.argsort(keys[idx], kind="stable")]
+
+
+def init_comm(sk, dist, rank, nranks):
+    """Give the context its NCCL communicator: rank 0 makes the id, torch.distributed carries it."""
+    from . import api
+    box = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    sk.comm_init(box[0], rank, nranks)
 
 
 class _DevArray:
@@ -142,9 +197,10 @@ class _nullcontext:
         return False
 
 
-def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks, host=True, dev_ptrs=None):
-    """The main.c stage script on a sharded snapshot.  sk: api.SkidGPU with set_shard/reduce cb applied.
-    Returns (labels by iOrder, catalogue, nUnbound, nGroupBefore)."""
+def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks, host=True, dev_ptrs=None,
+                     fetch=True):
+    """The main.c stage script on a sharded snapshot.  sk: api.SkidGPU with comm_init (or set_shard + reduce cb)
+    applied.  Returns (labels by iOrder, catalogue, nUnbound, nGroupBefore)."""
     from . import api
     f32 = lambda v: float(np.float32(v))
     tau = f32(flags["tau"])
@@ -155,7 +211,7 @@ def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks
     a32 = f32(1.0 / (1.0 + z))
     fCosmo = a32 * api.csmExp2Hub(a32, f32(flags["H0"]), f32(flags.get("Omega0", 1.0)), f32(flags.get("Lambda", 0.0)))
     sk.log = []
-    if host and nranks > 1 and reducer.device.type == "cuda":
+    if host and nranks > 1 and reducer is not None and reducer.device.type == "cuda":
         # the snapshot is replicated on the devices but need not cross PCIe N times: every rank uploads its
         # 1/N slice of the host AoS, transposes it to SoA columns on the device and the columns are
         # all-gathered over NVLink (N x fewer host->device bytes per rank)
@@ -167,22 +223,10 @@ def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks
     else:
         sk.set_particles_dev(dev_ptrs, len(pinit), nGas, nDark, nStar)
     sk.smDensityInit(flags["nSmooth"], flags.get("bGasAndDark", False), False, want_arrays=False)
-    sk.move(flags["fDensMin"], flags.get("fTempMax", api.FLT_MAX), api.FLT_MAX, fCvg, fStep)
-    dev = reducer.device
-
-    def gather_positions():
-        if nranks == 1 or sk.nMove == 0:
-            return
-        px, py, pz, nm, lo, hi = sk.mover_arrays()
-        sk.mask_unowned_movers()  # ownership is block-cyclic: the library zeroes what other ranks own
-        for p in (px, py, pz):
-            reducer.reduce_tensor(tensor_from_pointer(p, nm, 2, dev), 2)
-        if dev.type == "cuda":
-            torch.cuda.synchronize(dev)
-
-    gather_positions()
-    sk.kdFoF(tau)
-    sk.microstep(5, f32(0.1 * fStep))
-    gather_positions()
+    sk.move(flags["fDensMin"], flags.get("fTempMax", api.FLT_MAX), api.FLT_MAX, fCvg, fStep,
+            bNoPrune=flags.get("bNoPrune", False))
+    sk.kdFoF(tau)                      # the library exchanged the converged positions at the end of move
+    sk.microstep(5, f32(0.1 * fStep))  # ... and the micro-stepped ones here
     sk.kdCalcCenter(fetch=False)
-    return sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX, flags["nMembers"])
+    return sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, flags.get("nMaxMembers", api.INT_MAX),
+                       flags["nMembers"], fetch=fetch)

@@ -9,7 +9,8 @@ the build container, needs oracle/_ref):
 Stored per case in tests/golden/full_<name>.npz: the reference's log numbers (Ittr lines, groups before
 unbinding, unbound, groups), its stage times, the sorted group sizes, and for every STRIDE-th particle the
 canonical id of its group (= smallest member iOrder, 0-based, -1 for no group), which lets a test compute the
-same-group fraction on that sample without the reference's group numbering.
+same-group fraction on that sample without the reference's group numbering; and per final group its canonical id,
+member count and bound mass (the .gtp star record) for the bound-mass check.
 
 Usage:  python tests/golden/make_full_size_golden.py C2 [C3] [C5]
 """
@@ -56,14 +57,20 @@ def main():
                                          noprune=noprune, timeout=6 * 3600)
             log = refdump.parse_log(text)
             grp = tipsy.read_array(os.path.join(td, "ref.grp")).astype(np.int32)
+            gtp_mass = tipsy.read_gtp(os.path.join(td, "ref.gtp"), standard=True)["mass"]
         sizes = np.sort(np.bincount(grp)[1:])[::-1].astype(np.int32)
         canon = canonical_min_member(grp)
+        # per final group: canonical id (smallest member index), member count, bound mass from the .gtp
+        first = np.full(int(grp.max()) + 1, np.iinfo(np.int64).max, np.int64)
+        np.minimum.at(first, grp, np.arange(len(grp), dtype=np.int64))
+        group_table = dict(group_canon=first[1:].astype(np.int32), group_count=np.bincount(grp)[1:].astype(np.int32),
+                           group_mass=gtp_mass.astype(np.float32))
         np.savez_compressed(os.path.join(HERE, f"full_{name}.npz"),
                             log=np.array([len(log["ittr"]), log["nGroupBefore"], log["nUnbound"], log["nGroup"],
                                           log.get("nExtraScat", 0)], np.int64),
                             ittr=np.array(log["ittr"], np.int32), times=np.array(list(log["times"].values())),
                             time_names=np.array(list(log["times"].keys())), wall_s=wall, sizes=sizes,
-                            stride=stride, sample_canon=canon[::stride], n=n, seed=seed, kind=kind,
+                            stride=stride, sample_canon=canon[::stride], n=n, seed=seed, kind=kind, **group_table,
                             ref_args=" ".join(snap["ref_args"] + EXTRA_ARGS.get(name, []))
                             + (" [SKID_NOPRUNE=1]" if noprune else ""))
         print(name, "wall %.0f s" % wall, "log", len(log["ittr"]), log["nGroupBefore"], log["nUnbound"], log["nGroup"],

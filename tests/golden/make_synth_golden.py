@@ -2,7 +2,8 @@
 """Generate tests/golden/synth_golden.npz: results of the UNMODIFIED reference (oracle/_ref/skid_ref, built by
 oracle/build_ref.sh from /root/reference) on small synthetic boxes of skid_b200.synth (the generator of BASELINE
 configs 2-5).  Runs only in the build container.  Keys per case <name>: <name>_grp (final .grp), <name>_den,
-<name>_log = [nIttr lines, Groups before Unbind, particles Unbound, Number of Groups, nExtraScat].
+<name>_log = [nIttr lines, Groups before Unbind, particles Unbound, Number of Groups, nExtraScat], <name>_gtp_mass
+(bound mass per final group, numbering of <name>_grp).
 
 Usage:  python tests/golden/make_synth_golden.py
 """
@@ -37,6 +38,8 @@ def main():
             log = refdump.parse_log(text)
             out[name + "_grp"] = tipsy.read_array(os.path.join(td, "ref.grp")).astype(np.int32)
             out[name + "_den"] = tipsy.read_array(os.path.join(td, "ref.den")).astype(np.float32)
+            # bound masses of the final groups (the .gtp star records, kd.c:1665-1682), in the .grp's numbering
+            out[name + "_gtp_mass"] = tipsy.read_gtp(os.path.join(td, "ref.gtp"), standard=True)["mass"]
         out[name + "_log"] = np.array([len(log["ittr"]), log["nGroupBefore"], log["nUnbound"], log["nGroup"],
                                        log.get("nExtraScat", 0)], np.int64)
         print(name, out[name + "_log"])

@@ -1,0 +1,78 @@
+"""Unbinding of MASSIVE groups (>= 20 000 members; BASELINE configs[4]) on the GPU against golden results of the
+UNMODIFIED reference (tests/golden/massive_unbind_<case>.npz, made by make_massive_unbind_golden.py through the
+reference's own `-unbind` restart path, one process per group: kdInGroup + kdReadCenter + kdUnbind + kdTooSmall,
+main.c:349-373, kd.c:1299-1466, grav.c:8-135).
+
+Per group the same single-group catalogue goes through skidgpu_set_groups + skidgpu_unbind.  Asserted, per
+north_star: >= 99.9 % of the members keep / lose their membership like the reference, the bound mass agrees to 1e-4
+relative, and the removal count agrees up to the members whose final energy is within float rounding of zero (the
+loop stops at the first non-positive maximum, kd.c:1409, so a member at E ~ 0 can go either way; its removal
+changes every other energy by ~ m/M)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from skid_b200 import api, synth
+from skid_b200.tipsy import PGROUP_DTYPE
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(case):
+    path = os.path.join(GOLDEN, f"massive_unbind_{case}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated")
+    gold = np.load(path)
+    n = int(gold["n"])
+    snap = synth.make_box(n, seed=int(gold["seed"]), kind="massive", sigma_frac=float(gold["sigma_frac"]))
+    fl = snap["flags"]
+    tau = float(np.float32(fl["tau"]))
+    fScoop = float(np.float32(2.0 * tau))                           # main.c:344
+    fCosmo = 1.0 * api.csmExp2Hub(1.0, float(np.float32(fl["H0"])), 1.0, 0.0)   # z = 0: a = 1
+    sk = api.SkidGPU((fl["period"],) * 3, (0.0, 0.0, 0.0), bPeriodic=True)
+    report = []
+    try:
+        sk.set_particles(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"])
+        for k in range(int(gold["K"])):
+            members = gold[f"g{k}_members"]
+            ref_bound = np.unpackbits(gold[f"g{k}_bound"])[:len(members)].astype(bool)
+            labels = np.zeros(n, np.int32)
+            labels[members] = 1
+            cen = np.zeros(2, PGROUP_DTYPE)
+            cen["rCenter"][1] = gold[f"g{k}_centre"][0:3]
+            cen["vcm"][1] = gold[f"g{k}_centre"][3:6]
+            sk.set_groups(labels, 2, cen)
+            grp, cat, nUnbound, nBefore = sk.kdUnbind(1.0, 0.0, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX,
+                                                      fl["nMembers"])
+            assert nBefore == int(gold[f"g{k}_log"][0]) == 1
+            assert not grp[labels == 0].any()
+            bound = grp[members] != 0
+            same = float(np.mean(bound == ref_bound))
+            refU = int(gold[f"g{k}_log"][1])
+            ref_mass = gold[f"g{k}_gtp_mass"]
+            mass = float(cat["fMass"][1]) if len(cat) > 1 else 0.0
+            rm = float(ref_mass[0]) if len(ref_mass) else 0.0
+            report.append(dict(group=k, members=len(members), unbound=(nUnbound, refU), same=same, mass=(mass, rm),
+                               stage_ms=sk.stage_ms()["unbind"]))
+            assert same >= 0.999, report
+            assert abs(nUnbound - refU) <= max(2, int(1e-3 * len(members))), report
+            assert abs(mass - rm) <= 1e-4 * rm, report
+            if len(ref_mass):  # centre-of-mass velocity of the bound remnant (.gtp vel = vcm, kd.c:1670)
+                assert np.allclose(cat["vcm"][1], gold[f"g{k}_gtp_vel"][0], rtol=1e-3, atol=1e-4 * np.abs(gold[f"g{k}_gtp_vel"][0]).max()), report
+    finally:
+        sk.close()
+    print(case, report)
+    return report
+
+
+@pytest.mark.parametrize("case", ["m20", "m20hot"])
+def test_massive_group_unbinding_matches_reference(case):
+    _run_case(case)
+
+
+def test_massive_group_unbinding_config5():
+    """The five largest FoF groups of the C5 box (2^24, tau x 4): 553 566 / 285 401 / 281 461 / 145 081 /
+    144 725 members."""
+    _run_case("C5")

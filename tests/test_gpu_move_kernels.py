@@ -1,44 +1,24 @@
-"""The three implementations of the gradient walk (SKIDGPU_MOVE_KERNEL = tile | list | warp)
-evaluate the same (scatterer, mover) pairs with the same float32 hit test; they differ only in the
-summation order of the accelerations.  Each one runs in its own process (the switch is read once) on
-boxes chosen to exercise the tile path's special cases - periodic wraps (small N: a large fraction of
-the movers sits within 5 fStep of the box faces), dense cores with a large step (kind "massive":
+"""Regression (not parity): the two implementations of the gradient walk - the tile kernels (default) and the
+v1 kernel that walks the scatterer tree per mover and step (skidgpu_debug_move_kernel) - evaluate the same
+(scatterer, mover) pairs with the same float32 hit test; they differ only in the summation order of the
+accelerations.  Boxes are chosen to exercise the tile path's special cases - periodic wraps (small N: a large
+fraction of the movers sits within 5 fStep of the box faces), dense cores with a large step (kind "massive":
 short tiles, big list slots), gas+dark species - and must give the same trace and the same groups.
-The tile path is additionally checked against the live reference binary when it travelled."""
-import json
-import os
-import subprocess
-import sys
-
+The tile path is additionally checked against the live reference binary when it travelled (that one IS parity)."""
 import numpy as np
 import pytest
 
-from conftest import ROOT
+from oracle.refdump import canonical_labels
+from skid_b200 import api, synth
 
 pytestmark = pytest.mark.gpu
 
-CHILD = r"""
-import json, sys
-import numpy as np
-sys.path.insert(0, {root!r})
-from skid_b200 import api, synth
-from oracle.refdump import canonical_labels
-snap = synth.make_box(1 << {log2n}, seed={seed}, kind={kind!r})
-res = api.run_skid(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"], bNoPrune={noprune}, want_arrays=False,
-                   **snap["flags"])
-np.save({out!r}, canonical_labels(res["grp"]).astype(np.int32))
-print(json.dumps(dict(nMove=int(res["nMove"]), nIttr=int(res["nIttr"]), nGroupBefore=int(res["nGroupBefore"]),
-                      nUnbound=int(res["nUnbound"]), nGroup=int(res["nGroup"]), log=[list(map(int, l)) for l in res["log"]])))
-"""
 
-
-def run_kernel(tmp_path, kernel, log2n, kind, seed, noprune=False):
-    out = str(tmp_path / f"grp_{kernel}.npy")
-    env = dict(os.environ, SKIDGPU_MOVE_KERNEL=kernel)
-    code = CHILD.format(root=ROOT, log2n=log2n, seed=seed, kind=kind, noprune=noprune, out=out)
-    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    return json.loads(r.stdout.strip().splitlines()[-1]), np.load(out)
+def run_kernel(which, log2n, kind, seed, noprune=False):
+    snap = synth.make_box(1 << log2n, seed=seed, kind=kind)
+    res = api.run_skid(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"], bNoPrune=noprune, want_arrays=False,
+                       move_kernel=which, **snap["flags"])
+    return res, canonical_labels(res["grp"]).astype(np.int32)
 
 
 @pytest.mark.parametrize("log2n,kind,seed,noprune", [
@@ -48,25 +28,23 @@ def run_kernel(tmp_path, kernel, log2n, kind, seed, noprune=False):
     (16, "gasdark", 3, False),
     (16, "massive", 7, False),   # tau x 4: dense cores, short tiles
 ])
-def test_tile_list_warp_agree(tmp_path, log2n, kind, seed, noprune):
-    ref_info, ref_grp = run_kernel(tmp_path, "warp", log2n, kind, seed, noprune)
-    for k in ("tile", "list"):
-        info, grp = run_kernel(tmp_path, k, log2n, kind, seed, noprune)
-        assert info["nMove"] == ref_info["nMove"]
-        assert info["nIttr"] == ref_info["nIttr"], (k, info["nIttr"], ref_info["nIttr"])
-        assert info["nGroupBefore"] == ref_info["nGroupBefore"]
-        # Ittr trace: the active counts may differ by a few movers that sit exactly on the fCvg threshold
-        a = np.array([l[2] for l in info["log"] if l[0] == 0]), np.array([l[2] for l in ref_info["log"] if l[0] == 0])
-        assert len(a[0]) == len(a[1]) and np.all(np.abs(a[0] - a[1]) <= max(2, 1e-4 * a[1].max()))
-        same = float(np.mean(grp == ref_grp))
-        assert same >= 0.999, (k, same)
-        assert abs(info["nGroup"] - ref_info["nGroup"]) <= max(1, ref_info["nGroup"] // 200)
+def test_tile_and_walk_kernels_agree(log2n, kind, seed, noprune):
+    ref, ref_grp = run_kernel(1, log2n, kind, seed, noprune)
+    res, grp = run_kernel(0, log2n, kind, seed, noprune)
+    assert res["nMove"] == ref["nMove"]
+    assert res["nIttr"] == ref["nIttr"]
+    assert res["nGroupBefore"] == ref["nGroupBefore"]
+    # Ittr trace: the active counts may differ by a few movers that sit exactly on the fCvg threshold
+    a = np.array([l[2] for l in res["log"] if l[0] == 0]), np.array([l[2] for l in ref["log"] if l[0] == 0])
+    assert len(a[0]) == len(a[1]) and np.all(np.abs(a[0] - a[1]) <= max(2, 1e-4 * a[1].max()))
+    assert float(np.mean(grp == ref_grp)) >= 0.999
+    assert abs(res["nGroup"] - ref["nGroup"]) <= max(1, ref["nGroup"] // 200)
 
 
 def test_tile_matches_live_reference_small_box(tmp_path):
     """8192-particle periodic box (wrap-heavy) against the unmodified reference binary."""
     from oracle import refdump
-    from skid_b200 import synth, tipsy
+    from skid_b200 import tipsy
     if not refdump.have_ref():
         pytest.skip("oracle/_ref/skid_ref did not travel")
     snap = synth.make_box(1 << 13, seed=5, kind="dark")
@@ -75,8 +53,9 @@ def test_tile_matches_live_reference_small_box(tmp_path):
     out, _ = refdump.run_ref(f, snap["ref_args"], str(tmp_path / "ref"))
     log = refdump.parse_log(out)
     ref_grp = refdump.canonical_labels(tipsy.read_array(str(tmp_path / "ref.grp")).astype(np.int64))
-    info, grp = run_kernel(tmp_path, "tile", 13, "dark", 5)
-    assert info["nIttr"] == len(log["ittr"])
-    assert info["nGroupBefore"] == log["nGroupBefore"]
-    assert info["nGroup"] == log["nGroup"]
+    res, grp = run_kernel(0, 13, "dark", 5)
+    assert res["nIttr"] == len(log["ittr"])
+    assert [tuple(l[1:]) for l in res["log"] if l[0] == 0][0] == log["ittr"][0]
+    assert res["nGroupBefore"] == log["nGroupBefore"]
+    assert res["nGroup"] == log["nGroup"]
     assert float(np.mean(grp == ref_grp)) >= 0.999

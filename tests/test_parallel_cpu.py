@@ -111,3 +111,39 @@ def test_world2_gloo():
         assert res["active"] == 15
         assert res["labels"] == [0, 1, 0, 0, 2, 2, 3]
     assert out[0]["touched_sum"] == out[1]["touched_sum"]
+
+
+def test_block_cyclic_position_exchange_layout():
+    """numpy mirrors of k_owned_ids / k_pack_owned / k_unpack_all (csrc/move.cu): every mover has exactly one
+    owner, and packing the owned blocks + all-gather + unpacking restores every mover's value on every rank."""
+    for m in (1, 4095, 4096, 4097, 50000, 3 * parallel.OWN_BLOCK * 8 + 17):
+        for w in (1, 2, 3, 8):
+            owners = np.zeros(m, np.int64)
+            for r in range(w):
+                ids = parallel.owned_ids(m, r, w)
+                owners[ids] += 1
+                # the library's owned_count: whole blocks, the last one may be short
+                nb = -(-m // parallel.OWN_BLOCK)
+                cnt = sum((m - j * parallel.OWN_BLOCK) if j == nb - 1 else parallel.OWN_BLOCK for j in range(r, nb, w))
+                assert len(ids) == cnt
+            assert np.all(owners == 1)
+            x = np.random.default_rng(m + w).random(m).astype(np.float32)
+            slots = [parallel.pack_owned(x, r, w) for r in range(w)]
+            assert len({len(s) for s in slots}) == 1          # equal-sized all-gather blocks
+            assert np.array_equal(parallel.unpack_all(slots, m, w), x)
+
+
+def test_distributed_sort_pieces_equal_global_stable_sort():
+    """numpy mirror of dist_sort_pairs (csrc/tree.cu): key ranges from a regular sample, stable local sorts,
+    concatenation in rank order == one global stable sort, including heavy ties (group labels as keys)."""
+    rng = np.random.default_rng(5)
+    n = 1 << 19
+    for keys in (rng.integers(0, 1 << 62, n, dtype=np.int64).astype(np.uint64),
+                 rng.integers(0, 37, n).astype(np.uint64),                       # few distinct keys
+                 np.zeros(n, np.uint64)):                                        # all equal
+        want = np.argsort(keys, kind="stable")
+        for w in (2, 3, 8):
+            pieces = [parallel.dist_sort_piece(keys, r, w) for r in range(w)]
+            assert np.array_equal(np.concatenate(pieces), want)
+            if len(np.unique(keys)) > 1000:                   # balanced when the keys allow it
+                assert max(len(p) for p in pieces) < 1.1 * n / w
