@@ -23,7 +23,30 @@ def canonical_min_member(grp):
     return out.astype(np.int32)
 
 
-def compare(gold, grp, nIttr, nGroupBefore, nUnbound, nGroup):
+def compare_group_table(gold, grp, cat_mass):
+    """Bound masses at full size: groups are matched by (smallest member index, member count) against the
+    reference's per-group table (group_canon / group_count / group_mass from its .grp and .gtp); matched groups
+    must agree to 1e-4 relative in mass (north_star), and nearly all of the reference's groups must match."""
+    if "group_canon" not in gold:
+        return None
+    grp = np.asarray(grp, np.int64)
+    idx = np.nonzero(grp)[0]
+    first = np.full(int(grp.max()) + 1, len(grp), np.int64)
+    np.minimum.at(first, grp[idx], idx)
+    cnt = np.bincount(grp, minlength=int(grp.max()) + 1)
+    order = np.argsort(first[1:], kind="stable")
+    mine_canon, mine_cnt, mine_mass = first[1:][order], cnt[1:][order], np.asarray(cat_mass)[order]
+    rc, rn, rm = gold["group_canon"].astype(np.int64), gold["group_count"].astype(np.int64), gold["group_mass"]
+    pos = np.searchsorted(mine_canon, rc)
+    pos = np.minimum(pos, len(mine_canon) - 1)
+    hit = (mine_canon[pos] == rc) & (mine_cnt[pos] == rn)
+    rel = np.abs(mine_mass[pos][hit] - rm[hit]) / rm[hit]
+    assert rel.max() <= 1e-4, float(rel.max())
+    frac = float(hit.mean())
+    return dict(groups_matched=int(hit.sum()), groups_ref=len(rc), frac=frac, max_rel_mass=float(rel.max()))
+
+
+def compare(gold, grp, nIttr, nGroupBefore, nUnbound, nGroup, cat_mass=None):
     """north_star tolerances for the synthetic boxes: >= 99.9 % of the particles in the same group; the counters
     of the run agree with the reference's to a fraction of a per cent (they are identical on every box up to
     2^18, but a single mover converging one block later may shift them)."""
@@ -40,4 +63,8 @@ def compare(gold, grp, nIttr, nGroupBefore, nUnbound, nGroup):
     assert abs(nGroup - gG) <= max(1, gG // 1000), report
     assert abs(nUnbound - gU) <= max(2, gU // 100), report
     assert np.all(np.abs(sizes[:k].astype(np.int64) - gold["sizes"][:k]) <= np.maximum(2, gold["sizes"][:k] // 100)), report
+    if cat_mass is not None:
+        report["masses"] = compare_group_table(gold, grp, cat_mass)
+        if report["masses"] is not None:
+            assert report["masses"]["frac"] >= 0.95, report
     return report

@@ -26,7 +26,7 @@ def _run_case(case):
         pytest.skip(f"{path} not generated")
     gold = np.load(path)
     n = int(gold["n"])
-    snap = synth.make_box(n, seed=int(gold["seed"]), kind="massive", sigma_frac=float(gold["sigma_frac"]))
+    snap = synth.make_box(n, seed=int(gold["seed"]), kind="massive", sigma_frac=float(gold["sigma_frac"]) if "sigma_frac" in gold else 0.45)
     fl = snap["flags"]
     tau = float(np.float32(fl["tau"]))
     fScoop = float(np.float32(2.0 * tau))                           # main.c:344

@@ -1,9 +1,11 @@
-"""Sharded (one process per GPU, NCCL) pipeline vs the single-GPU pipeline.  Needs >= 2 GPUs;
-on a 1-GPU box it is skipped (run it with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`)."""
+"""Sharded pipeline (NCCL inside the library) against the single-GPU pipeline.  Needs >= 2 GPUs; on a 1-GPU box
+these are skipped (run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`; bench.py --gpus N
+repeats the comparison on every multi-GPU run and reports it as `parity`)."""
 import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -11,10 +13,15 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_sharded_equals_single_gpu():
+def _gpus():
     import torch
-    n = torch.cuda.device_count()
-    if n < 2:
+    return torch.cuda.device_count()
+
+
+def test_sharded_equals_single_gpu():
+    """One process per GPU (torchrun): demo, dark 2^18, gas+dark 2^16, massive 2^20 (distributed sorts), and the
+    demo through the callback shim."""
+    if _gpus() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
@@ -23,3 +30,31 @@ def test_sharded_equals_single_gpu():
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MULTI-GPU PARITY OK" in r.stdout
+
+
+def test_c_driver_gpus2_equals_gpus1(tmp_path):
+    """host/skid -gpus 2 (one process, one host thread per GPU, NCCL communicator made by the library) writes the
+    same catalogue as host/skid on one GPU."""
+    if _gpus() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from oracle.refdump import canonical_labels, parse_log
+    from skid_b200 import synth, tipsy
+    exe = os.path.join(ROOT, "host", "skid")
+    snap = synth.make_box(1 << 19, seed=21, kind="dark")
+    f = str(tmp_path / "in.std")
+    synth.write_std(snap, f)
+    outs = {}
+    for g in (1, 2):
+        pre = str(tmp_path / f"g{g}")
+        r = subprocess.run([exe] + snap["ref_args"] + ["-gpus", str(g), "-o", pre], stdin=open(f, "rb"), capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[g] = (parse_log(r.stdout), tipsy.read_array(pre + ".grp").astype(np.int64), tipsy.read_gtp(pre + ".gtp"))
+    a, b = outs[1], outs[2]
+    assert a[0]["ittr"][0] == b[0]["ittr"][0]
+    assert len(a[0]["ittr"]) == len(b[0]["ittr"])
+    assert a[0]["nGroupBefore"] == b[0]["nGroupBefore"]
+    assert abs(a[0]["nGroup"] - b[0]["nGroup"]) <= 1
+    assert float(np.mean(canonical_labels(a[1]) == canonical_labels(b[1]))) >= 0.9999
+    if a[0]["nGroup"] == b[0]["nGroup"]:
+        assert np.allclose(np.sort(a[2]["mass"]), np.sort(b[2]["mass"]), rtol=1e-4)

@@ -24,5 +24,6 @@ def test_full_size_box_matches_reference(name):
     if name == "C5":
         fl["nMaxMembers"] = 20000   # the golden's -maxgroup (make_full_size_golden.py: EXTRA_ARGS)
     res = api.run_skid(snap["pinit"], snap["nGas"], snap["nDark"], snap["nStar"], want_arrays=False, **fl)
-    rep = fullsize.compare(gold, res["grp"], res["nIttr"], res["nGroupBefore"], res["nUnbound"], res["nGroup"])
+    rep = fullsize.compare(gold, res["grp"], res["nIttr"], res["nGroupBefore"], res["nUnbound"], res["nGroup"],
+                           cat_mass=res["cat"]["fMass"][1:])
     print(name, rep)
