@@ -19,6 +19,7 @@ Usage:  python tests/golden/make_massive_unbind_golden.py <case> [K]
   case "m20hot": the same box with hotter halos (velocity dispersion x 1.8): a large unbound fraction, so the
               removal loop (arg-max, rcm/vcm update, kdSubPot) runs tens of thousands of times per group
   case "C5":  massive box 2^24 (seed 7, the C5 box): 553 566 / 285 401 / 281 461 / ... members, CPU hours
+  case "C5hot": the C5 box with hotter halos: tens of thousands of removals from groups of 10^5 .. 10^6 members
 Output tests/golden/massive_unbind_<case>.npz.
 """
 import os
@@ -35,7 +36,7 @@ sys.path.insert(0, ROOT)
 from oracle import refdump  # noqa: E402
 from skid_b200 import synth, tipsy  # noqa: E402
 
-CASES = {"m20": (1 << 20, 9, 0.45), "m20hot": (1 << 20, 9, 0.8), "C5": (1 << 24, 7, 0.45)}
+CASES = {"m20": (1 << 20, 9, 0.45), "m20hot": (1 << 20, 9, 0.8), "C5": (1 << 24, 7, 0.45), "C5hot": (1 << 24, 7, 0.8)}
 
 
 def write_grp(path, labels):
