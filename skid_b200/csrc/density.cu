@@ -5,9 +5,9 @@
 // smBallSearch (smooth1.c:41-129), the smDensityInit main loop (smooth1.c:150-277) and its
 // replica construction (smooth1.c:278-332).
 //
-// Design: one warp per query.  Queries run in Morton order, the 64 best candidates live in
-// registers (2 packed (d2,index) words per lane, sorted across the warp), new candidates are
-// staged in a 64-entry shared-memory buffer and merged 32 at a time with bitonic networks.
+// Design: one warp per query.  Queries run in Morton order, the k best candidates live in
+// registers (2, 4 or 8 packed (d2,index) words per lane for k <= 64 / 128 / 256, sorted across the warp), new
+// candidates are staged in a 64-entry shared-memory buffer and merged 32 at a time with bitonic networks.
 // The result is the k smallest by (d2, tree index): deterministic, independent of visit order.
 #include "ctx.cuh"
 #include <algorithm>
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_gather_sortedA(int m, const uint32_t *p
 	iordA[i] = (int)j;
 }
 
-// ------------------------------------------------------------------ warp-level k-best (k <= 64)
+// ------------------------------------------------------------------ warp-level k-best (k <= 32 R)
 #define KNN_INF 0x7f800000ffffffffull
 
 __device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
@@ -103,16 +103,36 @@ __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t v, int lane)
 	}
 	return v;
 }
-// A = (a0: ranks 0..31, a1: ranks 32..63) ascending; b = 32 unsorted candidates. Keeps the 64 smallest.
-__device__ __forceinline__ void kbest_merge(uint64_t &a0, uint64_t &a1, uint64_t b, int lane)
+// A = R registers per lane, a[r] holds ranks 32r .. 32r+31 ascending; b = 32 unsorted candidates.  Keeps the
+// 32 R smallest of A U b.  The new block cascades down from the top: against a[R-1] only its 32 smallest
+// survive, against every lower register the pair is split into a low and a high half; the cascade stops as
+// soon as everything still travelling is >= the next register's largest entry (the common case late in a
+// walk: new candidates sit just under the bound).
+template <int R> __device__ __forceinline__ void kbest_merge(uint64_t (&a)[R], uint64_t b, int lane)
 {
 	b = warp_sort32(b, lane);
-	uint64_t br = __shfl_sync(SK_FULL, b, 31 - lane);
-	uint64_t l = warp_bitonic_merge32(u64min(a1, br), lane); // 32 smallest of a1 U b, ascending
-	uint64_t lr = __shfl_sync(SK_FULL, l, 31 - lane);
-	uint64_t lo = u64min(a0, lr), hi = u64max(a0, lr);
-	a0 = warp_bitonic_merge32(lo, lane);
-	a1 = warp_bitonic_merge32(hi, lane);
+	uint64_t l = warp_bitonic_merge32(u64min(a[R - 1], __shfl_sync(SK_FULL, b, 31 - lane)), lane);
+#pragma unroll
+	for (int r = R - 2; r >= 0; --r) {
+		if (__shfl_sync(SK_FULL, l, 0) >= __shfl_sync(SK_FULL, a[r], 31)) {
+			a[r + 1] = l;
+			return;
+		}
+		const uint64_t lr = __shfl_sync(SK_FULL, l, 31 - lane);
+		const uint64_t lo = u64min(a[r], lr), hi = u64max(a[r], lr);
+		a[r + 1] = warp_bitonic_merge32(hi, lane);
+		l = warp_bitonic_merge32(lo, lane);
+	}
+	a[0] = l;
+}
+// d2 of the k-th best (+inf while fewer than k candidates are known)
+template <int R> __device__ __forceinline__ float kbest_kth(const uint64_t (&a)[R], int k)
+{
+	uint64_t v = a[0];
+#pragma unroll
+	for (int r = 1; r < R; ++r)
+		if (((k - 1) >> 5) == r) v = a[r];
+	return __uint_as_float((uint32_t)(__shfl_sync(SK_FULL, v, (k - 1) & 31) >> 32));
 }
 
 struct KnnArgs {
@@ -130,6 +150,7 @@ struct KnnArgs {
 };
 
 constexpr int KNN_WARPS = 8;
+constexpr int KNN_QPW = 8; // consecutive (Morton-adjacent) queries per warp, one after the other
 
 struct KnnQuery {
 	float x0, y0, z0, xp, xm, yp, ym, zp, zm, hx, hy, hz;
@@ -151,13 +172,34 @@ template <bool PER> __device__ __forceinline__ float knn_box_d2(const KnnQuery &
 	return dist2_rn(axis_gap(q.x0, lo.x, hi.x), axis_gap(q.y0, lo.y, hi.y), axis_gap(q.z0, lo.z, hi.z));
 }
 
-// Tree walk of one query (one warp).  Buckets [skipLo, skipHi] were merged before the walk.
-template <bool PER>
-__device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, uint64_t *s_buf, float (*s_dist)[32],
-                                         int lane, int skipLo, int skipHi, uint64_t &a0, uint64_t &a1, int &cnt,
-                                         float &bound)
+// Stage the lanes with `hit` (candidate idx at squared distance d2) in the warp's 64-entry buffer; 32 staged
+// candidates are merged into the k-best at once and the bound follows the k-th best.
+template <int R>
+__device__ __forceinline__ void knn_stage(bool hit, float d2, int idx, uint64_t *s_buf, int lane, int k, uint64_t (&a)[R],
+                                          int &cnt, float &bound)
 {
-	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t hm = __ballot_sync(SK_FULL, hit);
+	if (!hm) return;
+	if (hit) s_buf[cnt + __popc(hm & ((1u << lane) - 1u))] = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
+	cnt += __popc(hm);
+	__syncwarp();
+	if (cnt >= 32) {
+		const uint64_t b = s_buf[lane];
+		kbest_merge<R>(a, b, lane);
+		const uint64_t t = (lane + 32 < cnt) ? s_buf[lane + 32] : KNN_INF;
+		__syncwarp();
+		s_buf[lane] = t;
+		__syncwarp();
+		cnt -= 32;
+		bound = fminf(bound, kbest_kth<R>(a, k));
+	}
+}
+
+// Tree walk of one query (one warp).  Buckets [skipLo, skipHi] were merged before the walk.
+template <bool PER, int R>
+__device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, uint64_t *s_buf, float (*s_dist)[32],
+                                         int lane, int skipLo, int skipHi, uint64_t (&best)[R], int &cnt, float &bound)
+{
 	const int n = a.n, k = a.k;
 	int lev = a.tv.top - 1;
 	uint32_t node = 0;
@@ -198,24 +240,7 @@ __device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, ui
 			bool valid = idx < n;
 			float4 p = a.pos4[valid ? idx : 0];
 			float d2 = knn_d2<PER>(q, p);
-			bool hit = valid && d2 <= bound;
-			uint32_t hm = __ballot_sync(SK_FULL, hit);
-			if (hm) {
-				if (hit) s_buf[cnt + __popc(hm & lt)] = ((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx;
-				cnt += __popc(hm);
-				__syncwarp();
-				if (cnt >= 32) {
-					uint64_t b = s_buf[lane];
-					kbest_merge(a0, a1, b, lane);
-					uint64_t t = (lane + 32 < cnt) ? s_buf[lane + 32] : KNN_INF;
-					__syncwarp();
-					s_buf[lane] = t;
-					__syncwarp();
-					cnt -= 32;
-					uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
-					bound = fminf(bound, __uint_as_float((uint32_t)(kth >> 32)));
-				}
-			}
+			knn_stage<R>(valid && d2 <= bound, d2, idx, s_buf, lane, k, best, cnt, bound);
 			continue;
 		}
 		// upper levels: nearest child box first as well, so that the walk starts in the subtree that holds
@@ -238,97 +263,112 @@ __device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, ui
 #undef KNN_TEST_CHILDREN
 }
 
-__global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
+// One warp takes KNN_QPW consecutive queries.  From the second one on, the k neighbours of the previous query
+// (a Morton neighbour, typically a fraction of the ball radius away) are k distinct candidates, so the largest of
+// their distances to the new query is an upper bound of its k-th distance before anything else is known: the
+// phase-A buckets and the walk then only stage what can still enter, and a query needs ~k/32 + 1 merges instead
+// of ~10 (the merges were 39 % of the kernel's instructions, profiles/r01_v6_knn_2e22_lines.txt).
+template <int R> __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 {
 	__shared__ uint64_t s_buf[KNN_WARPS][64];
 	__shared__ float s_dist[KNN_WARPS][SK_MAXLEV][32];
 	const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int qi = a.qLo + blockIdx.x * KNN_WARPS + w;
-	if (qi >= a.qHi) return;
 	const int n = a.n, k = a.k;
-	const float4 qp = a.pos4[qi];
-	KnnQuery q;
-	q.x0 = qp.x;
-	q.y0 = qp.y;
-	q.z0 = qp.z;
-	q.xp = __fadd_rn(qp.x, a.L[0]);
-	q.xm = __fsub_rn(qp.x, a.L[0]);
-	q.yp = __fadd_rn(qp.y, a.L[1]);
-	q.ym = __fsub_rn(qp.y, a.L[1]);
-	q.zp = __fadd_rn(qp.z, a.L[2]);
-	q.zm = __fsub_rn(qp.z, a.L[2]);
-	q.hx = a.hL[0];
-	q.hy = a.hL[1];
-	q.hz = a.hL[2];
-
-	// Phase A: the query's own bucket and its two Morton neighbours hold most of the k nearest;
-	// merging them first gives a tight bound (the k-th best of >= 64 real candidates) before the walk.
-	uint64_t a0 = KNN_INF, a1 = KNN_INF;
 	const int nB = (n + 31) >> 5;
-	int b0 = (qi >> 5) - 1;
-	if (b0 > nB - 3) b0 = nB - 3;
-	if (b0 < 0) b0 = 0;
-	const int b1 = b0 + 2 < nB - 1 ? b0 + 2 : nB - 1;
-	for (int b = b0; b <= b1; ++b) {
-		int idx = b * 32 + lane;
-		bool valid = idx < n;
-		float4 p = a.pos4[valid ? idx : 0];
-		float d2 = knn_d2<true>(q, p);
-		uint64_t c = valid ? (((uint64_t)__float_as_uint(d2) << 32) | (uint32_t)idx) : KNN_INF;
-		kbest_merge(a0, a1, c, lane);
-	}
-	float bound;
-	{
-		uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
-		bound = __uint_as_float((uint32_t)(kth >> 32)); // +inf while fewer than k candidates are known
-	}
-	int cnt = 0;
-	// Phase B: walk the tree for everything else inside the bound.  If the ball cannot reach a face
-	// of the periodic box no image can be closer than the point itself: plain differences are then
-	// bit-identical to the min-image ones and much cheaper.
-	const float r0 = sqrtf(bound) * 1.000001f;
-	const bool per = !(q.x0 - r0 >= a.boxLo[0] && q.x0 + r0 <= a.boxHi[0] && q.y0 - r0 >= a.boxLo[1] &&
-	                   q.y0 + r0 <= a.boxHi[1] && q.z0 - r0 >= a.boxLo[2] && q.z0 + r0 <= a.boxHi[2]);
-	if (per) knn_walk<true>(a, q, s_buf[w], s_dist[w], lane, b0, b1, a0, a1, cnt, bound);
-	else knn_walk<false>(a, q, s_buf[w], s_dist[w], lane, b0, b1, a0, a1, cnt, bound);
-	if (cnt > 0) {
-		uint64_t b = (lane < cnt) ? s_buf[w][lane] : KNN_INF;
-		kbest_merge(a0, a1, b, lane);
-	}
-	const uint64_t kth = (k > 32) ? __shfl_sync(SK_FULL, a1, k - 33) : __shfl_sync(SK_FULL, a0, k - 1);
-	const float fBall2 = __uint_as_float((uint32_t)(kth >> 32));
-	if (lane == 0) a.ball2[qi] = fBall2;
+	uint64_t best[R];
+	bool havePrev = false;
+	const long long q0 = (long long)a.qLo + ((long long)blockIdx.x * KNN_WARPS + w) * KNN_QPW;
+	for (int t = 0; t < KNN_QPW; ++t) {
+		const long long qll = q0 + t;
+		if (qll >= a.qHi) break;
+		const int qi = (int)qll;
+		const float4 qp = a.pos4[qi];
+		KnnQuery q;
+		q.x0 = qp.x;
+		q.y0 = qp.y;
+		q.z0 = qp.z;
+		q.xp = __fadd_rn(qp.x, a.L[0]);
+		q.xm = __fsub_rn(qp.x, a.L[0]);
+		q.yp = __fadd_rn(qp.y, a.L[1]);
+		q.ym = __fsub_rn(qp.y, a.L[1]);
+		q.zp = __fadd_rn(qp.z, a.L[2]);
+		q.zm = __fsub_rn(qp.z, a.L[2]);
+		q.hx = a.hL[0];
+		q.hy = a.hL[1];
+		q.hz = a.hL[2];
 
-	// ---- density (smooth1.c:249-263): every PQ entry except the farthest (pqHead)
-	const float ih2 = __fdiv_rn(4.0f, fBall2);                                          // (float)(4.0/h2)
-	const float fNorm = (float)(0.5 * 0.318309886183790671538 * sqrt((double)ih2) * (double)ih2);
-	const float mi = qp.w;
-	double gsum = 0.0;
+		float bound = __uint_as_float(0x7f800000u);
+		if (havePrev) {
+			uint32_t mb = 0u; // non-negative floats order like their bit patterns
 #pragma unroll
-	for (int r = 0; r < 2; ++r) {
-		int e = r * 32 + lane;
-		uint64_t ent = r ? a1 : a0;
-		int j = (int)(uint32_t)ent;
-		float key = __uint_as_float((uint32_t)(ent >> 32));
-		if (e < k - 1) {
-			float r2 = __fmul_rn(key, ih2);
-			float rs = (float)(2.0 - sqrt((double)r2));
-			if (r2 < 1.0f) rs = (float)(1.0 - 0.75 * (double)rs * (double)r2);
-			else rs = (float)(0.25 * (double)rs * (double)rs * (double)rs);
-			rs = __fmul_rn(rs, fNorm);
-			float mj = a.pos4[j].w;
-			gsum += (double)__fmul_rn(rs, mj);
-			atomicAdd(&a.rho64[j], (double)__fmul_rn(rs, mi));
+			for (int r = 0; r < R; ++r)
+				if (r * 32 + lane < k) mb = max(mb, __float_as_uint(knn_d2<true>(q, a.pos4[(uint32_t)best[r]])));
+			bound = __uint_as_float(__reduce_max_sync(SK_FULL, mb));
 		}
-		if (a.nbr && e < k) {
-			size_t row = (size_t)a.iord[qi] * k + e;
-			a.nbr[row] = a.iord[j];
-			a.nbrD2[row] = key;
+#pragma unroll
+		for (int r = 0; r < R; ++r) best[r] = KNN_INF;
+		int cnt = 0;
+		// Phase A: the query's own bucket and its Morton neighbours (R + 1 buckets >= k candidates) hold most of
+		// the k nearest.
+		int b0 = (qi >> 5) - R / 2;
+		if (b0 > nB - (R + 1)) b0 = nB - (R + 1);
+		if (b0 < 0) b0 = 0;
+		const int b1 = b0 + R < nB - 1 ? b0 + R : nB - 1;
+		for (int b = b0; b <= b1; ++b) {
+			const int idx = b * 32 + lane;
+			const bool valid = idx < n;
+			const float4 p = a.pos4[valid ? idx : 0];
+			const float d2 = knn_d2<true>(q, p);
+			knn_stage<R>(valid && d2 <= bound, d2, idx, s_buf[w], lane, k, best, cnt, bound);
 		}
+		// Phase B: walk the tree for everything else inside the bound.  If the ball cannot reach a face
+		// of the periodic box no image can be closer than the point itself: plain differences are then
+		// bit-identical to the min-image ones and much cheaper.
+		const float r0 = sqrtf(bound) * 1.000001f;
+		const bool per = !(q.x0 - r0 >= a.boxLo[0] && q.x0 + r0 <= a.boxHi[0] && q.y0 - r0 >= a.boxLo[1] &&
+		                   q.y0 + r0 <= a.boxHi[1] && q.z0 - r0 >= a.boxLo[2] && q.z0 + r0 <= a.boxHi[2]);
+		if (per) knn_walk<true, R>(a, q, s_buf[w], s_dist[w], lane, b0, b1, best, cnt, bound);
+		else knn_walk<false, R>(a, q, s_buf[w], s_dist[w], lane, b0, b1, best, cnt, bound);
+		if (cnt > 0) {
+			const uint64_t b = (lane < cnt) ? s_buf[w][lane] : KNN_INF;
+			kbest_merge<R>(best, b, lane);
+		}
+		__syncwarp();
+		havePrev = true;
+		const float fBall2 = kbest_kth<R>(best, k);
+		if (lane == 0) a.ball2[qi] = fBall2;
+
+		// ---- density (smooth1.c:249-263): every PQ entry except the farthest (pqHead)
+		const float ih2 = __fdiv_rn(4.0f, fBall2);                                          // (float)(4.0/h2)
+		const float fNorm = (float)(0.5 * 0.318309886183790671538 * sqrt((double)ih2) * (double)ih2);
+		const float mi = qp.w;
+		double gsum = 0.0;
+#pragma unroll
+		for (int r = 0; r < R; ++r) {
+			const int e = r * 32 + lane;
+			const uint64_t ent = best[r];
+			const int j = (int)(uint32_t)ent;
+			const float key = __uint_as_float((uint32_t)(ent >> 32));
+			if (e < k - 1) {
+				float r2 = __fmul_rn(key, ih2);
+				float rs = (float)(2.0 - sqrt((double)r2));
+				if (r2 < 1.0f) rs = (float)(1.0 - 0.75 * (double)rs * (double)r2);
+				else rs = (float)(0.25 * (double)rs * (double)rs * (double)rs);
+				rs = __fmul_rn(rs, fNorm);
+				float mj = a.pos4[j].w;
+				gsum += (double)__fmul_rn(rs, mj);
+				atomicAdd(&a.rho64[j], (double)__fmul_rn(rs, mi));
+			}
+			if (a.nbr && e < k) {
+				size_t row = (size_t)a.iord[qi] * k + e;
+				a.nbr[row] = a.iord[j];
+				a.nbrD2[row] = key;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(SK_FULL, gsum, o);
+		if (lane == 0) atomicAdd(&a.rho64[qi], gsum);
 	}
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(SK_FULL, gsum, o);
-	if (lane == 0) atomicAdd(&a.rho64[qi], gsum);
 }
 
 __global__ void __launch_bounds__(256) k_density_finish(int m, const int *iordA, const double *rho64,
@@ -466,7 +506,7 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	cudaStream_t s = c.stream;
 	const int n = c.n;
 	if (n <= 0) throw SkidError("skidgpu_density: no particles set");
-	if (nSmooth < 1 || nSmooth > 64) throw SkidError("skidgpu_density: nSmooth must be in [1,64]");
+	if (nSmooth < 1 || nSmooth > 256) throw SkidError("skidgpu_density: nSmooth must be in [1,256] (the k best live in 2, 4 or 8 registers per lane)");
 	StageTimer tm(c, 0);
 	c.nSmooth = nSmooth;
 	c.bGasAndDark = bGasAndDark;
@@ -537,8 +577,12 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	c.kernel_ms[KF_KNN] = 0;
 	c.kernel_launches[KF_KNN] = 0;
 	c.spans.begin(KF_KNN, s);
-	if (ka.qHi > ka.qLo)
-		SK_LAUNCH(k_knn_density, (unsigned)ceil_div(ka.qHi - ka.qLo, KNN_WARPS), KNN_WARPS * 32, 0, s, ka);
+	if (ka.qHi > ka.qLo) {
+		const unsigned grid = (unsigned)ceil_div(ka.qHi - ka.qLo, KNN_WARPS * KNN_QPW);
+		if (nSmooth <= 64) SK_LAUNCH(k_knn_density<2>, grid, KNN_WARPS * 32, 0, s, ka);
+		else if (nSmooth <= 128) SK_LAUNCH(k_knn_density<4>, grid, KNN_WARPS * 32, 0, s, ka);
+		else SK_LAUNCH(k_knn_density<8>, grid, KNN_WARPS * 32, 0, s, ka);
+	}
 	c.spans.end(s);
 	sk_allgather(c, ka.ball2, chunk, SK_F32);
 	sk_reduce(c, ka.rho64, m, SK_F64, SK_SUM);

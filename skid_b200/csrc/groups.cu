@@ -825,18 +825,14 @@ __global__ void __launch_bounds__(256)
 	softS[i] = soft[j];
 }
 
-__global__ void __launch_bounds__(256) k_set_pstart(int nGroup, const int *gN, skidgpu_pgroup *cat)
+// catalogue bookkeeping fields (pStart/pCurr, kd.c:1213-1219) from the exclusive scan of the member counts
+__global__ void __launch_bounds__(256) k_set_pstart(int nGroup, const int *gN, const uint32_t *scan, skidgpu_pgroup *cat)
 {
-	// serial prefix over groups is fine for the catalogue bookkeeping fields (pStart/pCurr, kd.c:1213-1219)
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		int p = 0;
-		for (int g = 0; g < nGroup; ++g) {
-			cat[g].nMembers = gN[g];
-			cat[g].pStart = p;
-			p += gN[g];
-			cat[g].pCurr = p;
-		}
-	}
+	int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= nGroup) return;
+	cat[g].nMembers = gN[g];
+	cat[g].pStart = (int)scan[g];
+	cat[g].pCurr = (int)scan[g] + gN[g];
 }
 
 __global__ void __launch_bounds__(256) k_count_members(int n, const int *gid, int *gN)
@@ -1065,7 +1061,8 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 		double *acc = c.gAcc.alloc((size_t)(G2 + 1) * GA_STRIDE); // scratch only
 		(void)acc;
 		SK_LAUNCH(k_count_members, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, gN);
-		SK_LAUNCH(k_set_pstart, 1, 32, 0, s, G2, gN, c.gCat.p);
+		exclusive_scan_u32((const uint32_t *)gN, scan, G2, c.ws, s); // counts are non-negative
+		SK_LAUNCH(k_set_pstart, (unsigned)ceil_div(G2, 256), 256, 0, s, G2, gN, scan, c.gCat.p);
 		SK_LAUNCH(k_group_radius, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, c.x.p, c.y.p, c.z.p, c.L[0], c.L[1],
 		          c.L[2], c.gCat.p);
 	}

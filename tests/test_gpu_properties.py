@@ -118,14 +118,14 @@ def test_edge_cases():
     sk = api.SkidGPU((1.0,) * 3, (0.0,) * 3, bPeriodic=True)
     sk.set_particles(snap["pinit"], 0, 4096, 0)
     prev = None
-    for k in (8, 32, 33, 64):
+    for k in (8, 32, 33, 64, 65, 128, 200, 256):
         rho, b2 = sk.smDensityInit(k)
         assert np.all(b2 > 0)
         if prev is not None:
             assert np.all(b2 >= prev)
         prev = b2
     with pytest.raises(api.SkidError):
-        sk.smDensityInit(65)
+        sk.smDensityInit(257)
     with pytest.raises(api.SkidError):
         sk.smDensityInit(0)
     sk.close()
@@ -155,3 +155,29 @@ def test_native_format_input(tmp_path):
         gtp = tipsy.read_gtp(str(tmp_path / ("s.gtp" if std else "n.gtp")), standard=std)
         assert len(gtp["mass"]) == int(outs[std].max())
     assert np.array_equal(outs[True], outs[False])
+
+
+@pytest.mark.parametrize("k", [2, 7, 32, 33, 64, 65, 96, 128, 129, 256])
+def test_knn_against_brute_force_oracle(k):
+    """The man page tells users not to go below nSmooth = 64 for high-resolution runs (man1/skid.1), so larger -s
+    values are normal use: every k up to 256 against the oracle's brute-force search (oracle/skid_oracle.c
+    orc_knn_density, itself pinned to the reference's kNN dump at k = 64): fBall2 bit for bit, identical neighbour
+    sets inside the ball, identical sorted distances, density within 1e-5."""
+    from oracle import orc
+    n = 6000
+    snap = synth.make_box(n, seed=77, kind="dark")
+    p = snap["pinit"]
+    ball2_ref, rho_ref, nbr_ref, d2_ref = orc.knn_density(p["r"], p["fMass"], k, 1.0, want_nbr=True)
+    sk = api.SkidGPU((1.0,) * 3, (0.0,) * 3, bPeriodic=True)
+    try:
+        sk.set_particles(p, 0, n, 0)
+        rho, b2 = sk.smDensityInit(k, keep_neighbors=True)
+        nbr, d2 = sk.neighbors()
+    finally:
+        sk.close()
+    assert np.array_equal(b2.view(np.uint32), ball2_ref.view(np.uint32))
+    assert np.array_equal(np.sort(d2, axis=1).view(np.uint32), np.sort(d2_ref, axis=1).view(np.uint32))
+    for i in range(0, n, 7):
+        assert set(nbr[i][d2[i] < b2[i]].tolist()) == set(nbr_ref[i][d2_ref[i] < ball2_ref[i]].tolist()), i
+    if k > 1:
+        assert (np.abs(rho - rho_ref) / rho_ref).max() <= 1e-5

@@ -1,6 +1,7 @@
+# usage: tools/gpu_ncu_call.sh <tag> <kernel-regex> <log2n> <kind> [launch-skip] [launch-count]
+# one `ncu --set full` capture of the named kernel(s) on one pass of the hot path; report lands in gpurun_out/
 mkdir -p gpurun_out
-timeout 140 ncu --set full --clock-control none --import-source on -k regex:"k_tile_walk|k_tile_step" --launch-skip 2 --launch-count 2 \
-  -f -o gpurun_out/r01_v7_tilewalk_tilestep_2e24 python tools/ncu_driver.py 24 gasdark > gpurun_out/ncu_a.log 2>&1; echo "ncu A rc=$?"
-timeout 110 ncu --set full --clock-control none --import-source on -k regex:"k_stat_groups|k_stat_keys" --launch-count 2 \
-  -f -o gpurun_out/r01_v7_stats_2e24 python tools/ncu_driver.py 24 gasdark > gpurun_out/ncu_b.log 2>&1; echo "ncu B rc=$?"
-tail -3 gpurun_out/ncu_a.log gpurun_out/ncu_b.log; ls -la gpurun_out/*.ncu-rep
+TAG=$1; KRE=$2; LOG2N=${3:-24}; KIND=${4:-gasdark}; SKIP=${5:-0}; CNT=${6:-1}
+timeout 280 ncu --set full --clock-control none --import-source on -k regex:"$KRE" --launch-skip $SKIP --launch-count $CNT \
+  -f -o gpurun_out/$TAG python tools/ncu_driver.py $LOG2N $KIND > gpurun_out/$TAG.log 2>&1; echo "ncu $TAG rc=$?"
+tail -2 gpurun_out/$TAG.log; ls -la gpurun_out/$TAG.ncu-rep
