@@ -9,6 +9,7 @@
 // 1/r rounded to float32 ("dir"), float32 products G*m*dir, float64 accumulation.  No tensor
 // cores: this is an O(n^2) scalar-potential sum, not a dense contraction.
 #include "ctx.cuh"
+#include <cooperative_groups.h>
 
 // per-group f64 accumulators
 #define GA_MASS 0
@@ -376,10 +377,20 @@ template <int MODE> __global__ void __launch_bounds__(256) k_scoop(const ScoopAr
 	if (!MODE && lane == 0) a.cnt[g] = count;
 }
 
-// Potential of every group member: pairs within the group (kdCellPot) + scoop sources
-// (kdAddScoopPot).  One block of POT_T threads per tile of POT_T members; the group's members and
-// scoop sources stream through shared memory.
+// Potential of every group member: pairs within the group (kdCellPot) + scoop sources (kdAddScoopPot).
+// One block of POT_T threads per tile I of POT_T members.  Like the reference's i < j loop (grav.c:14-34) every
+// pair is evaluated ONCE: the block walks the tiles J >= I of its group; the diagonal tile is a plain loop, an
+// off-diagonal tile is swept by rotation (thread i meets column (i + t) mod POT_T at step t), the row terms go
+// to a register and the column terms to a per-warp shared array, so no two lanes touch the same column at the
+// same step.  Per-pair arithmetic is the reference's (float32 geometry, dir, float32 product G*m*dir, float64
+// sums); a tile's partial sums reach the float64 potential with one atomic per member.
+// ncu on the massive-halo box (config 5, profiles/r02_*): the two-sided loop that evaluated every pair twice was
+// 523 ms of a 1025 ms pass (5.4e11 warp instructions, issue bound).
 constexpr int POT_T = 128;
+// per-tile partial sums stay in float64 like the reference's accumulator (grav.c:31-32): the loosely bound small
+// groups sit at E ~ 0, where a float32 partial sum (1e-7 relative) flips removals - measured on the 2^21 box:
+// 560 672 particles unbound instead of the reference's 567 192 (float64: 567 19x)
+typedef double pot_acc_t;
 
 struct PotArgs {
 	int nGroup;
@@ -399,12 +410,20 @@ struct PotArgs {
 	int nMaxMembers;
 };
 
+__device__ __forceinline__ float pair_dir(float d2, float twoh, bool spline, int iSoftType)
+{
+	float dir = far_dir(d2);
+	if (!(spline && d2 >= fmaxf(twoh * twoh, 1.0e-30f))) dir = soft_dir(d2, twoh, iSoftType); // inside the softening, or Plummer
+	return dir;
+}
+
 __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 {
 	__shared__ float4 s_r[POT_T];
 	__shared__ float s_m[POT_T];
+	__shared__ double s_col[POT_T / 32][POT_T];
 	__shared__ int s_g;
-	const int tid = threadIdx.x;
+	const int tid = threadIdx.x, w = tid >> 5;
 	if (tid == 0) {
 		// find the group of this tile: largest g with tileStart[g] <= blockIdx.x
 		int lo = 1, hi = a.nGroup - 1;
@@ -419,32 +438,64 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 	const int g = s_g;
 	const int beg = a.gStart[g], n = a.gStart[g + 1] - beg;
 	if (n >= a.nMaxMembers) return; // kd.c:1330
-	const int i = (blockIdx.x - a.tileStart[g]) * POT_T + tid;
+	const int I = (int)(blockIdx.x - a.tileStart[g]);
+	const int i = I * POT_T + tid;
 	const bool act = i < n;
 	const bool spline = a.iSoftType != SKIDGPU_PLUMMER;
 	float4 ri = make_float4(0, 0, 0, 0);
-	if (act) ri = a.qr[beg + i];
+	float gmi = 0.0f;
+	if (act) {
+		ri = a.qr[beg + i];
+		gmi = __fmul_rn(a.G, a.qv[beg + i].w); // kd->G*p[i].fMass (grav.c:31-32), float
+	}
 	double pot = 0.0;
-	for (int j0 = 0; j0 < n; j0 += POT_T) {
-		int j = j0 + tid;
+	const int nT = (n + POT_T - 1) / POT_T;
+	for (int J = I; J < nT; ++J) {
+		const int j = J * POT_T + tid;
 		if (j < n) {
 			s_r[tid] = a.qr[beg + j];
-			s_m[tid] = __fmul_rn(a.G, a.qv[beg + j].w); // kd->G*p[j].fMass (grav.c:31-32), float
+			s_m[tid] = __fmul_rn(a.G, a.qv[beg + j].w);
+		} else {
+			s_r[tid] = make_float4(3.0e18f, 3.0e18f, 3.0e18f, 0.0f); // far away, massless
+			s_m[tid] = 0.0f;
 		}
+#pragma unroll
+		for (int c = 0; c < POT_T / 32; ++c) s_col[w][c * 32 + (tid & 31)] = 0.0;
 		__syncthreads();
-		int lim = n - j0 < POT_T ? n - j0 : POT_T;
-		if (act) {
+		pot_acc_t rowp = 0;
+		if (J == I) { // diagonal tile: every member against every other member of the same tile
+			const int lim = n - J * POT_T < POT_T ? n - J * POT_T : POT_T;
+			if (act) {
 #pragma unroll 4
-			for (int t = 0; t < lim; ++t) {
-				const float4 rj = s_r[t];
+				for (int t = 0; t < lim; ++t) {
+					const float4 rj = s_r[t];
+					const float dx = __fsub_rn(ri.x, rj.x), dy = __fsub_rn(ri.y, rj.y), dz = __fsub_rn(ri.z, rj.z);
+					const float d2 = dist2_rn(dx, dy, dz);
+					const float dir = t == tid ? 0.0f : pair_dir(d2, __fadd_rn(ri.w, rj.w), spline, a.iSoftType);
+					rowp += (pot_acc_t)__fmul_rn(s_m[t], dir);
+				}
+			}
+		} else { // off-diagonal tile: each pair once, both sides credited
+			double *col = s_col[w];
+#pragma unroll 4
+			for (int t = 0; t < POT_T; ++t) {
+				const int c = (tid + t) & (POT_T - 1);
+				const float4 rj = s_r[c];
 				const float dx = __fsub_rn(ri.x, rj.x), dy = __fsub_rn(ri.y, rj.y), dz = __fsub_rn(ri.z, rj.z);
 				const float d2 = dist2_rn(dx, dy, dz);
-				const float twoh = __fadd_rn(ri.w, rj.w);
-				float dir = far_dir(d2);
-				if (!(spline && d2 >= fmaxf(twoh * twoh, 1.0e-30f))) // inside the softening, Plummer, or the particle itself
-					dir = (j0 + t == i) ? 0.0f : soft_dir(d2, twoh, a.iSoftType);
-				pot += (double)__fmul_rn(s_m[t], dir);
+				const float dir = pair_dir(d2, __fadd_rn(ri.w, rj.w), spline, a.iSoftType);
+				rowp += (pot_acc_t)__fmul_rn(s_m[c], dir);        // padding columns are massless
+				col[c] += (double)__fmul_rn(gmi, dir);            // inactive rows are massless
+				__syncwarp();
 			}
+		}
+		pot += (double)rowp;
+		__syncthreads();
+		if (J != I) {
+			double cs = 0.0;
+#pragma unroll
+			for (int ww = 0; ww < POT_T / 32; ++ww) cs += s_col[ww][tid];
+			if (j < n) atomicAdd(&a.pot[beg + j], cs);
 		}
 		__syncthreads();
 	}
@@ -466,20 +517,19 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 		__syncthreads();
 		int lim = (int)(sn - j0 < (uint32_t)POT_T ? sn - j0 : (uint32_t)POT_T);
 		if (act) {
+			pot_acc_t rowp = 0;
 #pragma unroll 4
 			for (int t = 0; t < lim; ++t) {
 				const float4 rj = s_r[t];
 				const float dx = __fsub_rn(rj.x, ri.x), dy = __fsub_rn(rj.y, ri.y), dz = __fsub_rn(rj.z, ri.z);
 				const float d2 = dist2_rn(dx, dy, dz);
-				const float twoh = __fadd_rn(rj.w, ri.w);
-				float dir = far_dir(d2);
-				if (!(spline && d2 >= fmaxf(twoh * twoh, 1.0e-30f))) dir = soft_dir(d2, twoh, a.iSoftType);
-				pot += (double)__fmul_rn(s_m[t], dir);
+				rowp += (pot_acc_t)__fmul_rn(s_m[t], pair_dir(d2, __fadd_rn(rj.w, ri.w), spline, a.iSoftType));
 			}
+			pot += (double)rowp;
 		}
 		__syncthreads();
 	}
-	if (act) a.pot[beg + i] = pot;
+	if (act) atomicAdd(&a.pot[beg + i], pot); // other blocks add their column sums to the same entry
 }
 
 // The removal loop of kdUnbind (kd.c:1360-1457).  One block per group.
@@ -498,9 +548,14 @@ struct UnbArgs {
 	unsigned int *nUnbound;
 	unsigned long long *nPairs;
 	int rank, nranks;
+	int nSmallMax; // groups of this many members or more are left to k_unbind_cl
 };
 
 constexpr int UNB_T = 256;
+constexpr int UNB_MID = 1024;   // >= this many members: one block of UCL_T threads per group (k_unbind_cl<1>)
+constexpr int UNB_BIG = 16384;  // >= this many: a thread-block cluster of UCL_NB blocks per group (k_unbind_cl<UCL_NB>)
+constexpr int UCL_T = 1024;
+constexpr int UCL_NB = 8;
 
 __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 {
@@ -508,7 +563,7 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const int beg = a.gStart[g];
 	int n = a.gStart[g + 1] - beg;
-	if (n >= a.nMaxMembers || n <= 0 || (g % a.nranks) != a.rank) return;
+	if (n >= a.nMaxMembers || n <= 0 || n >= a.nSmallMax || (g % a.nranks) != a.rank) return;
 	float4 *qr = a.qr + beg, *qv = a.qv + beg;
 	int *qord = a.qord + beg;
 	double *pot = a.pot + beg;
@@ -689,6 +744,285 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 			atomicAdd(&a.gN[0], nRemoved);
 		}
 	}
+}
+
+// The same loop for large groups.  One block per group is a single SM chasing memory latency (measured: 96 us
+// per removal in a 39 k-member group); here a group gets UCL_T threads, or a thread-block CLUSTER of NB blocks
+// whose partial arg-max / arg-min meet through distributed shared memory, and a removal costs ONE pass over the
+// members: the removed particle's potential is subtracted (kdSubPot) and the new energy is formed in the same
+// sweep, with rcm/vcm already updated (they only depend on the removed particle, kd.c:1430-1434).  The order of
+// removals, the tie rule (first index of the largest energy, kd.c:1400-1403) and the swap-to-end bookkeeping are
+// the reference's.  Members are re-read through L2 (__ldcg): the swap is written by another SM of the cluster.
+template <int NB> __device__ __forceinline__ float4 ucl_ld4(const float4 *p) { return NB > 1 ? __ldcg(p) : *p; }
+template <int NB> __device__ __forceinline__ double ucl_ldd(const double *p) { return NB > 1 ? __ldcg(p) : *p; }
+
+template <int NB> __global__ void __launch_bounds__(UCL_T) k_unbind_cl(const UnbArgs a, const int *list)
+{
+	namespace cg = cooperative_groups;
+	cg::cluster_group cl = cg::this_cluster();
+	const int brank = NB > 1 ? (int)cl.block_rank() : 0;
+	const int g = list[blockIdx.x / NB];
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	constexpr int NW = UCL_T / 32;
+	const int NT = NB * UCL_T, t0 = brank * UCL_T + tid;
+	const int beg = a.gStart[g];
+	int n = a.gStart[g + 1] - beg;
+	float4 *qr = a.qr + beg, *qv = a.qv + beg;
+	int *qord = a.qord + beg;
+	double *pot = a.pot + beg;
+	__shared__ double s_red[NW][7];
+	__shared__ double s_part[7];
+	__shared__ double s_cm[7]; // dMass, rcm[3], vcm[3]
+	__shared__ float s_wv[2][NW];
+	__shared__ int s_wi[2][NW];
+	__shared__ float s_xv[2][2]; // [parity][best, least] of this block, read by the other blocks of the cluster
+	__shared__ int s_xi[2][2];
+	__shared__ float s_fv;
+	__shared__ int s_fi[2];
+	__shared__ float4 s_rem[2];
+
+	// centre of mass (kd.c:1360-1375), float64 sums of float32 products
+	{
+		double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+		for (int i = t0; i < n; i += NT) {
+			const float4 r = qr[i], v = qv[i];
+			acc[0] += (double)v.w;
+			acc[1] += (double)__fmul_rn(v.w, r.x);
+			acc[2] += (double)__fmul_rn(v.w, r.y);
+			acc[3] += (double)__fmul_rn(v.w, r.z);
+			acc[4] += (double)__fmul_rn(v.w, v.x);
+			acc[5] += (double)__fmul_rn(v.w, v.y);
+			acc[6] += (double)__fmul_rn(v.w, v.z);
+		}
+#pragma unroll
+		for (int k = 0; k < 7; ++k) {
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(SK_FULL, acc[k], o);
+			if (lane == 0) s_red[w][k] = acc[k];
+		}
+		__syncthreads();
+		if (tid < 7) {
+			double t = 0.0;
+			for (int ww = 0; ww < NW; ++ww) t += s_red[ww][tid];
+			s_part[tid] = t;
+		}
+		if (NB > 1) cl.sync();
+		else __syncthreads();
+		if (tid == 0) {
+			double t[7] = {0, 0, 0, 0, 0, 0, 0};
+			for (int r = 0; r < NB; ++r) {
+				const double *rp = NB > 1 ? cl.map_shared_rank(s_part, r) : s_part;
+				for (int k = 0; k < 7; ++k) t[k] += rp[k];
+			}
+			s_cm[0] = t[0];
+			for (int k = 1; k < 7; ++k) s_cm[k] = t[k] / t[0];
+		}
+		__syncthreads();
+	}
+
+	int nRemoved = 0, iMinFinal = 0, par = 0;
+	bool sub = false;
+	float4 rs = make_float4(0, 0, 0, 0);
+	float gms = 0.0f;
+	while (true) {
+		// one sweep: (kdSubPot of the particle removed last, grav.c:39-60) + energy scan (kd.c:1389-1408)
+		const double rcx = s_cm[1], rcy = s_cm[2], rcz = s_cm[3], vcx = s_cm[4], vcy = s_cm[5], vcz = s_cm[6];
+		float best = -1.0f, least = 1.0f;
+		int bi = 0x7fffffff, li = 0x7fffffff;
+		for (int i = t0; i < n; i += NT) {
+			const float4 r = ucl_ld4<NB>(qr + i), v = ucl_ld4<NB>(qv + i);
+			double p = ucl_ldd<NB>(pot + i);
+			if (sub) {
+				const float dx = __fsub_rn(rs.x, r.x), dy = __fsub_rn(rs.y, r.y), dz = __fsub_rn(rs.z, r.z);
+				const float d2 = dist2_rn(dx, dy, dz);
+				p -= (double)__fmul_rn(gms, pair_dir(d2, __fadd_rn(rs.w, r.w), a.iSoftType != SKIDGPU_PLUMMER, a.iSoftType));
+				pot[i] = p;
+			}
+			const float dvx = (float)((double)a.fShift * ((double)v.x - vcx) + (double)a.fCosmo * ((double)r.x - rcx));
+			const float dvy = (float)((double)a.fShift * ((double)v.y - vcy) + (double)a.fCosmo * ((double)r.y - rcy));
+			const float dvz = (float)((double)a.fShift * ((double)v.z - vcz) + (double)a.fCosmo * ((double)r.z - rcz));
+			const float dv2 = __fadd_rn(__fadd_rn(__fadd_rn(0.0f, __fmul_rn(dvx, dvx)), __fmul_rn(dvy, dvy)), __fmul_rn(dvz, dvz));
+			const float fTot = (float)(0.5 * (double)dv2 - p * (1.0 + (double)a.z));
+			if (fTot > best) {
+				best = fTot;
+				bi = i;
+			}
+			if (fTot < least) {
+				least = fTot;
+				li = i;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			const float ob = __shfl_xor_sync(SK_FULL, best, o);
+			const int obi = __shfl_xor_sync(SK_FULL, bi, o);
+			if (ob > best || (ob == best && obi < bi)) {
+				best = ob;
+				bi = obi;
+			}
+			const float ol = __shfl_xor_sync(SK_FULL, least, o);
+			const int oli = __shfl_xor_sync(SK_FULL, li, o);
+			if (ol < least || (ol == least && oli < li)) {
+				least = ol;
+				li = oli;
+			}
+		}
+		if (lane == 0) {
+			s_wv[0][w] = best;
+			s_wi[0][w] = bi;
+			s_wv[1][w] = least;
+			s_wi[1][w] = li;
+		}
+		__syncthreads();
+		if (w == 0) {
+			best = s_wv[0][lane];
+			bi = s_wi[0][lane];
+			least = s_wv[1][lane];
+			li = s_wi[1][lane];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) {
+				const float ob = __shfl_xor_sync(SK_FULL, best, o);
+				const int obi = __shfl_xor_sync(SK_FULL, bi, o);
+				if (ob > best || (ob == best && obi < bi)) {
+					best = ob;
+					bi = obi;
+				}
+				const float ol = __shfl_xor_sync(SK_FULL, least, o);
+				const int oli = __shfl_xor_sync(SK_FULL, li, o);
+				if (ol < least || (ol == least && oli < li)) {
+					least = ol;
+					li = oli;
+				}
+			}
+			if (lane == 0) {
+				s_xv[par][0] = best;
+				s_xi[par][0] = bi;
+				s_xv[par][1] = least;
+				s_xi[par][1] = li;
+			}
+		}
+		if (NB > 1) {
+			cl.sync();
+			if (w == 0) { // the blocks' partial results through distributed shared memory
+				const int r = lane < NB ? lane : 0;
+				best = *cl.map_shared_rank(&s_xv[par][0], r);
+				bi = *cl.map_shared_rank(&s_xi[par][0], r);
+				least = *cl.map_shared_rank(&s_xv[par][1], r);
+				li = *cl.map_shared_rank(&s_xi[par][1], r);
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) {
+					const float ob = __shfl_xor_sync(SK_FULL, best, o);
+					const int obi = __shfl_xor_sync(SK_FULL, bi, o);
+					if (ob > best || (ob == best && obi < bi)) {
+						best = ob;
+						bi = obi;
+					}
+					const float ol = __shfl_xor_sync(SK_FULL, least, o);
+					const int oli = __shfl_xor_sync(SK_FULL, li, o);
+					if (ol < least || (ol == least && oli < li)) {
+						least = ol;
+						li = oli;
+					}
+				}
+			}
+		}
+		if (tid == 0) {
+			if (bi == 0x7fffffff) bi = 0; // nothing exceeded the initial -1.0 (kd.c:1389-1390)
+			if (li == 0x7fffffff) li = 0;
+			s_fv = best;
+			s_fi[0] = bi;
+			s_fi[1] = li;
+			if (!(best < 0.0f || a.bNoUnbind)) { // every block keeps the removed particle before it is swapped away
+				s_rem[0] = ucl_ld4<NB>(qr + bi);
+				s_rem[1] = ucl_ld4<NB>(qv + bi);
+			}
+		}
+		__syncthreads();
+		const float fBig = s_fv;
+		const int iBig = s_fi[0];
+		iMinFinal = s_fi[1];
+		if (fBig < 0.0f || a.bNoUnbind) break; // kd.c:1409
+		rs = s_rem[0];
+		const float4 vs = s_rem[1];
+		gms = __fmul_rn(a.G, vs.w);
+		if (NB > 1) cl.sync(); // all blocks have read particle iBig
+		const int nn = n - 1;
+		if (brank == 0 && tid == 0) { // unbind particle iBig (kd.c:1413-1440): label, swap with the last member
+			a.gid[qord[iBig]] = 0;
+			if (nn > 0 && iBig != nn) {
+				const float4 tr = qr[nn], tv = qv[nn];
+				const int to = qord[nn];
+				const double tp = pot[nn];
+				qr[nn] = rs;
+				qv[nn] = vs;
+				qord[nn] = qord[iBig];
+				pot[nn] = pot[iBig];
+				qr[iBig] = tr;
+				qv[iBig] = tv;
+				qord[iBig] = to;
+				pot[iBig] = tp;
+			}
+			__threadfence();
+		}
+		if (tid == 0) { // every block updates its copy of the centre of mass with the same arithmetic
+			if (nn == 0) {
+				s_cm[0] = 0.0;
+				s_cm[4] = s_cm[5] = s_cm[6] = 0.0;
+			} else {
+				const double dM = s_cm[0] - (double)vs.w;
+				s_cm[0] = dM;
+				const double f = (double)vs.w / dM;
+				s_cm[1] += f * (s_cm[1] - (double)rs.x);
+				s_cm[2] += f * (s_cm[2] - (double)rs.y);
+				s_cm[3] += f * (s_cm[3] - (double)rs.z);
+				s_cm[4] += f * (s_cm[4] - (double)vs.x);
+				s_cm[5] += f * (s_cm[5] - (double)vs.y);
+				s_cm[6] += f * (s_cm[6] - (double)vs.z);
+			}
+		}
+		n = nn;
+		++nRemoved;
+		par ^= 1;
+		sub = a.bSubPot != 0; // kdSubPot only for pure dark / pure star inputs (kd.c:1441)
+		if (NB > 1) cl.sync(); // the swap is visible to every block
+		else __syncthreads();
+		if (nn == 0) break;
+	}
+	if (brank == 0 && tid == 0) {
+		skidgpu_pgroup *pg = &a.cat[g];
+		pg->fMass = (float)s_cm[0];
+		pg->vcm[0] = (float)s_cm[4];
+		pg->vcm[1] = (float)s_cm[5];
+		pg->vcm[2] = (float)s_cm[6];
+		const float4 rb = qr[iMinFinal];
+		const float rr[3] = {rb.x, rb.y, rb.z};
+		const float t2 = __fmul_rn(2.0f, a.hx);
+		for (int j = 0; j < 3; ++j) { // kd.c:1452-1457 (hx for all three axes, as the reference)
+			float dx = __fadd_rn(rr[j], pg->rel[j]);
+			if (dx > a.hx) dx = __fsub_rn(dx, t2);
+			if (dx <= -a.hx) dx = __fadd_rn(dx, t2);
+			pg->rBound[j] = dx;
+		}
+		pg->nMembers = n;
+		a.gN[g] = n;
+		if (nRemoved) {
+			atomicAdd(a.nUnbound, (unsigned int)nRemoved);
+			atomicAdd(&a.gN[0], nRemoved);
+		}
+	}
+	if (NB > 1) cl.sync(); // nobody leaves while its shared memory may still be read
+}
+
+// groups by size class for the removal loop: list[0 ..) = one block each, list[nGroup ..) = one cluster each
+__global__ void __launch_bounds__(256)
+    k_unbind_classes(int nGroup, const int *gN, int nMax, int rank, int nranks, int *list, unsigned int *counts)
+{
+	int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= nGroup || g == 0 || (g % nranks) != rank) return;
+	const int n = gN[g];
+	if (n >= nMax || n < UNB_MID) return;
+	if (n >= UNB_BIG) list[nGroup + atomicAdd(&counts[2], 1u)] = g;
+	else list[atomicAdd(&counts[1], 1u)] = g;
 }
 
 // kdTooSmall (kd.c:1251-1293)
@@ -1013,7 +1347,32 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			ua.nPairs = nullptr;
 			ua.rank = c.rank;
 			ua.nranks = c.nranks;
+			ua.nSmallMax = UNB_MID;
+			// size classes: small groups one 256-thread block each, large ones 1024 threads, the largest a cluster
+			DevBuf<int> clsList;
+			clsList.alloc(2 * (size_t)G + 2);
+			SK_LAUNCH(k_unbind_classes, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, nMaxMembers, c.rank, c.nranks,
+			          clsList.p, dCnt.p);
+			unsigned int hCls[4] = {0, 0, 0, 0};
+			CK(cudaMemcpyAsync(hCls, dCnt.p, sizeof hCls, cudaMemcpyDeviceToHost, s));
+			CK(cudaStreamSynchronize(s));
 			SK_LAUNCH(k_unbind, (unsigned)(G - 1), UNB_T, 0, s, ua);
+			if (hCls[1] > 0) SK_LAUNCH(k_unbind_cl<1>, hCls[1], UCL_T, 0, s, ua, (const int *)clsList.p);
+			if (hCls[2] > 0) {
+				cudaLaunchConfig_t cfg = {};
+				cfg.gridDim = dim3(hCls[2] * UCL_NB);
+				cfg.blockDim = dim3(UCL_T);
+				cfg.stream = s;
+				cudaLaunchAttribute at[1];
+				at[0].id = cudaLaunchAttributeClusterDimension;
+				at[0].val.clusterDim.x = UCL_NB;
+				at[0].val.clusterDim.y = 1;
+				at[0].val.clusterDim.z = 1;
+				cfg.attrs = at;
+				cfg.numAttrs = 1;
+				CK(cudaLaunchKernelEx(&cfg, k_unbind_cl<UCL_NB>, ua, (const int *)(clsList.p + G)));
+				++g_skid_launches;
+			}
 			if (c.nranks > 1) { // merge the shards: labels (owner wrote 0 for unbound members), rows, count
 				DevBuf<float> pack;
 				DevBuf<int> cpack;
