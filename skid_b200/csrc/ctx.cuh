@@ -110,7 +110,6 @@ struct skidgpu_ctx {
 	DevBuf<float> mx, my, mz, rox, roy, roz;
 	DevBuf<int> mOrd; // mover id -> iOrder
 	DevBuf<uint32_t> actList, actList2;
-	DevBuf<uint32_t> mQueue; // movers that take this step with their own tree walk (move.cu)
 	// tiles: TILE consecutive entries of the position-sorted active list share one scatterer list (move.cu)
 	int nTiles = 0, tileStepsLeft = 0, tileWindow = 5, tileBuilds = 0, superCap = 2048;
 	DevBuf<uint64_t> tKeys;

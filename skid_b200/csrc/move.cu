@@ -188,8 +188,6 @@ struct StepArgs {
 	float L[3];
 	double wrapLo[3], wrapHi[3];
 	float *a0x, *a0y, *a0z; // nullable: keep accelerations
-	uint32_t *queue;      // movers that take this step with their own tree walk (left their tile's reach)
-	uint32_t *queueCount; // = dT + 2, reset by k_update_T
 	float wrapHiF[3], wrapLoF[3]; // largest floats <= wrapHi / wrapLo: same decisions as the double compares
 	// tiles (k_tile_build / k_tile_step): TILE consecutive entries of the position-sorted active list
 	uint32_t *tList; // nTiles small slots (TILE_CAP), then nBig big slots (BIG_CAP) from bigBase
@@ -344,7 +342,6 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 			cnt += nc_;                                                                    \
 		}                                                                                      \
 	}
-constexpr int AUX_BLOCKS = 148 * 4; // persistent grid of the queue-driven fallback kernel
 
 __device__ __forceinline__ uint64_t spread21m(uint32_t v)
 {
@@ -648,6 +645,9 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a)
 	int cap = TILE_CAP;
 	int cnt = 0;
 	{
+		// (A two-pass variant - bounding-box pretest of the tile, survivors compacted in shared memory, member test
+		// on the dense survivors - was measured and dropped: the box of 8 members rejects too little of the
+		// supertile's superset to pay for the compaction; list builds 117 -> 135 ms per pass.)
 		bool overflow = false;
 		for (int s0 = 0; s0 < ns && !overflow; s0 += 32) {
 			const uint32_t e = eN;
@@ -669,6 +669,63 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a)
 		a.tCnt[t] = cnt;
 		a.tOff[t] = off;
 	}
+}
+
+// One mover against the whole scatterer tree (one warp): smBallGather + smAccDensity + the move.  The v1 design
+// (profiles/r01_v1_move_*: ~3600 warp instructions per mover-step, 1500 scatterers tested for 85 hits); it now
+// serves the few movers a tile cannot (left the reach of their tile's list: a periodic wrap moves them by L, or
+// their tile's list overflowed) and the skidgpu_debug_move_kernel test hook.
+__device__ __forceinline__ void walk_one_mover(const StepArgs &a, const uint32_t id, const float T, const int lane)
+{
+	const float x = a.mx[id], y = a.my[id], z = a.mz[id];
+	float ax = 0.0f, ay = 0.0f, az = 0.0f;
+	float rmin = 3.0e38f;
+	int lev = a.tv.top - 1;
+	uint32_t node = 0;
+	uint32_t mymask = 0;
+#define STEP_TEST_CHILDREN()                                                                           \
+	{                                                                                              \
+		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
+		float4 lo = bx[0], hi = bx[1];                                                         \
+		bool in_ = x >= lo.x && x <= hi.x && y >= lo.y && y <= hi.y && z >= lo.z && z <= hi.z && \
+		           lo.w >= T;                                                                  \
+		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
+		if (lane == lev) mymask = m_;                                                          \
+	}
+	STEP_TEST_CHILDREN();
+	while (true) {
+		uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
+		if (m == 0) {
+			++lev;
+			if (lev >= a.tv.top) break;
+			node >>= 5;
+			continue;
+		}
+		int c = __ffs(m) - 1;
+		m &= m - 1;
+		if (lane == lev) mymask = m;
+		uint32_t child = node * 32 + c;
+		if (lev > 0) {
+			--lev;
+			node = child;
+			STEP_TEST_CHILDREN();
+			continue;
+		}
+		const uint32_t e = child * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+		const float4 p = a.entPos[e];
+		// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
+		const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
+		const float d2 = dist2_rn(dx, dy, dz);
+		if (d2 < p.w) {
+			const float4 q = a.entNR[e];
+			if (q.z >= T) {
+				ACC_HIT(dx, dy, dz, d2, q);
+				if (a.touched) a.touched[e] = 1;
+			}
+		}
+	}
+#undef STEP_TEST_CHILDREN
+	finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
 }
 
 // ncu on the first k_tile_step (one warp per mover, profiles/r01_v5_tilestep_*): issue bound at 606
@@ -701,7 +758,6 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 		const float ox = x - b.x, oy = y - b.y, oz = z - b.z;
 		inside = ox * ox + oy * oy + oz * oz <= b.w * b.w;
 	}
-	if (have && !inside && j == 0) a.queue[atomicAdd(a.queueCount, 1u)] = id; // overflowed tile, or left its ball: own walk
 	const bool run = have && inside;
 	const uint32_t *list = a.tList + a.tOff[t];
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
@@ -741,96 +797,53 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 		rmin = fminf(rmin, __shfl_xor_sync(SK_FULL, rmin, o));
 	}
 	if (run && j == 0) finish_mover(a, id, x, y, z, ax, ay, az, rmin);
+	// members the list cannot serve (overflowed tile, or left its reach) take the step with their own tree walk,
+	// one after the other on this warp: rare, and hidden behind the other tiles of the launch
+	uint32_t own = __ballot_sync(SK_FULL, have && !inside && j == 0);
+	while (own) {
+		const int src = __ffs(own) - 1;
+		own &= own - 1;
+		walk_one_mover(a, __shfl_sync(SK_FULL, id, src), T, threadIdx.x & 31);
+	}
 }
 
-// One block per tile; the grid is sized from the host's upper bound of the active count.
+// After a step: adopt the new threshold (ScatterCut, smooth1.c:509-513).  If nothing was hit the
+// reference's fScatDens stays 0.0 and nothing is cut.  Also resets the per-step counters and adds the step's
+// active movers to the stage's mover-step counter.
+__device__ __forceinline__ void update_T(uint32_t *dT, int bNoPrune, int par, int launched)
+{
+	uint32_t nx = dT[DT_MIN];
+	if (!bNoPrune && nx != T_NONE) dT[DT_T] = nx;
+	dT[DT_MIN] = T_NONE;
+	dT[DT_QUEUE] = 0u;
+	dT[DT_TILEQ] = 0u;
+	dT[4] = 0u;
+	dT[DT_TICKET] = 0u; // ticket counter of k_tile_walk
+	if (launched) *(unsigned long long *)(dT + DT_STEPS) += dT[DT_NACT + par];
+}
+__global__ void k_update_T(uint32_t *dT, int bNoPrune, int par, int launched) { update_T(dT, bNoPrune, par, launched); }
+
+// One block per tile; the grid is sized from the host's upper bound of the active count.  (Letting the last
+// block to finish adopt the step's threshold instead of launching k_update_T was measured and dropped: the
+// completion count - even two-level, 256 blocks per word - and its fences cost every one of the ~10^6 small
+// blocks more than the launch it saves: k_tile_step 164 -> 175 ms per pass.)
 __global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
 {
 	__shared__ TileShared sh;
 	__shared__ uint32_t sh_e[TILE_CHUNK];
 	const int t = blockIdx.x;
-	if (t * TILE >= N_ACTIVE(a)) return;
-	tile_step_body(a, t, sh, sh_e);
+	if (t * TILE < N_ACTIVE(a)) tile_step_body(a, t, sh, sh_e);
 }
 
-// v1 kernel: one warp per mover walks the scatterer tree every step (profiles/r01_v1_move_*: issue
-// bound, ~3600 warp instructions per mover-step, 1500 scatterers tested for 85 hits).  Still used for
-// the movers a tile can not serve (queue filled by k_tile_step) and, with SKIDGPU_MOVE_KERNEL=warp,
-// for everything (A/B measurements).  countPtr == nullptr: the first `count` entries of `ids`.
+// Test hook (skidgpu_debug_move_kernel): every active mover takes the step with its own tree walk.
 constexpr int STEP_WARPS = 8;
-__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a, const uint32_t *ids, int count,
-                                                               const uint32_t *countPtr)
+__global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a, const uint32_t *ids, const uint32_t *countPtr)
 {
 	const int lane = threadIdx.x & 31;
-	const int n = countPtr ? (int)*countPtr : count;
+	const int n = (int)*countPtr;
 	const float T = __uint_as_float(a.dT[0]);
-	for (int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5); wi < n; wi += gridDim.x * STEP_WARPS) {
-		const uint32_t id = ids[wi];
-		const float x = a.mx[id], y = a.my[id], z = a.mz[id];
-		float ax = 0.0f, ay = 0.0f, az = 0.0f;
-		float rmin = 3.0e38f;
-		int lev = a.tv.top - 1;
-		uint32_t node = 0;
-		uint32_t mymask = 0;
-#define STEP_TEST_CHILDREN()                                                                           \
-	{                                                                                              \
-		const float4 *bx = a.tv.box[lev] + 2 * ((size_t)node * 32 + lane);                     \
-		float4 lo = bx[0], hi = bx[1];                                                         \
-		bool in_ = x >= lo.x && x <= hi.x && y >= lo.y && y <= hi.y && z >= lo.z && z <= hi.z && \
-		           lo.w >= T;                                                                  \
-		uint32_t m_ = __ballot_sync(SK_FULL, in_);                                             \
-		if (lane == lev) mymask = m_;                                                          \
-	}
-		STEP_TEST_CHILDREN();
-		while (true) {
-			uint32_t m = __shfl_sync(SK_FULL, mymask, lev);
-			if (m == 0) {
-				++lev;
-				if (lev >= a.tv.top) break;
-				node >>= 5;
-				continue;
-			}
-			int c = __ffs(m) - 1;
-			m &= m - 1;
-			if (lane == lev) mymask = m;
-			uint32_t child = node * 32 + c;
-			if (lev > 0) {
-				--lev;
-				node = child;
-				STEP_TEST_CHILDREN();
-				continue;
-			}
-			const uint32_t e = child * 32 + lane; // arrays are padded with fBall2 = -1 dummies
-			const float4 p = a.entPos[e];
-			// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
-			const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
-			const float d2 = dist2_rn(dx, dy, dz);
-			if (d2 < p.w) {
-				const float4 q = a.entNR[e];
-				if (q.z >= T) {
-					ACC_HIT(dx, dy, dz, d2, q);
-					if (a.touched) a.touched[e] = 1;
-				}
-			}
-		}
-#undef STEP_TEST_CHILDREN
-		finish_step(a, id, x, y, z, ax, ay, az, rmin, lane);
-	}
-}
-
-// After a step: adopt the new threshold (ScatterCut, smooth1.c:509-513).  If nothing was hit the
-// reference's fScatDens stays 0.0 and nothing is cut.  Also resets the per-step queues and adds the step's
-// active movers to the stage's mover-step counter.
-__global__ void k_update_T(uint32_t *dT, int bNoPrune, int par, int launched)
-{
-	uint32_t nx = dT[DT_MIN];
-	if (!bNoPrune && nx != T_NONE) dT[DT_T] = nx;
-	dT[DT_MIN] = T_NONE;
-	dT[DT_QUEUE] = 0u; // own-walk movers of the next step
-	dT[DT_TILEQ] = 0u;
-	dT[4] = 0u;
-	dT[DT_TICKET] = 0u; // ticket counter of k_tile_walk
-	if (launched) *(unsigned long long *)(dT + DT_STEPS) += dT[DT_NACT + par];
+	for (int wi = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5); wi < n; wi += gridDim.x * STEP_WARPS)
+		walk_one_mover(a, ids[wi], T, lane);
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
@@ -946,8 +959,6 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 		sa.wrapLo[d] = (double)c.C[d] - 0.5 * (double)c.L[d]; // kd.c:726
 	}
 	sa.a0x = sa.a0y = sa.a0z = nullptr;
-	sa.queue = c.mQueue.p;
-	sa.queueCount = c.dT.p ? c.dT.p + DT_QUEUE : nullptr;
 	for (int d = 0; d < 3; ++d) { // r > t  <=>  r > (largest float <= t) for float r (same for <=)
 		float h = (float)sa.wrapHi[d], l = (float)sa.wrapLo[d];
 		if ((double)h > sa.wrapHi[d]) h = nextafterf(h, -INFINITY);
@@ -1079,12 +1090,9 @@ static void one_step(skidgpu_ctx &c, StepArgs &sa, int bNoPrune)
 			c.spans.begin(KF_TILE_STEP, s);
 			SK_LAUNCH(k_tile_step, (unsigned)ceil_div(bound, TILE), TILE_THREADS, 0, s, sa);
 			c.spans.end(s);
-			c.spans.begin(KF_FALLBACK, s);
-			SK_LAUNCH(k_move_step, AUX_BLOCKS, STEP_WARPS * 32, 0, s, sa, sa.queue, 0, sa.queueCount);
-			c.spans.end(s);
 		} else { // test hook: a tree walk per mover and step (the v1 kernel)
 			unsigned g = (unsigned)ceil_div(bound, STEP_WARPS);
-			SK_LAUNCH(k_move_step, g > 148u * 64u ? 148u * 64u : g, STEP_WARPS * 32, 0, s, sa, sa.act, 0,
+			SK_LAUNCH(k_move_step, g > 148u * 64u ? 148u * 64u : g, STEP_WARPS * 32, 0, s, sa, sa.act,
 			          (const uint32_t *)(c.dT.p + DT_NACT + c.actPar));
 		}
 	}
@@ -1169,7 +1177,6 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		c.roz.alloc(m);
 		c.mOrd.alloc(m);
 		const int own = c.nOwned;
-		c.mQueue.alloc(own > 0 ? own : 1);
 		{
 			const size_t nt = ceil_div(own > 0 ? own : 1, TILE);
 			// list offsets are 32-bit: 8.3 M tiles (67 M movers on ONE GPU) would overflow them - fail loudly
