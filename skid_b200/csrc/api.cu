@@ -188,6 +188,7 @@ static void set_counts(skidgpu_ctx *c, int n, int nGas, int nDark, int nStar)
 	c->nGroup = 0;
 	c->nEnt = c->nExtra = c->nAct = 0;
 	c->haveCenters = false;
+	c->haveRhoStat = false;
 	if (n > c->reservedFor) { // first pass at this size: grow the pool in one piece, not buffer by buffer
 		size_t freeB = 0, totalB = 0;
 		// measured footprint of the hot path: ~250 B/particle replicated (input, trees, scatterers)

@@ -73,6 +73,8 @@ struct skidgpu_ctx {
 	int reservedFor = 0; // largest particle count the memory pool was pre-grown for (api.cu set_counts)
 	DevBuf<float> x, y, z, vx, vy, vz, mass, soft, temp;
 	DevBuf<float> rho, ball2; // by iOrder; 0 for non scatter-active
+	DevBuf<float> rhoStat;    // rho with the scatterers cut at step 0 zeroed (what kdOutStats reads after -fic)
+	bool haveRhoStat = false;
 	DevBuf<skidgpu_pinit> aos; // staging for the AoS upload
 	Workspace ws;
 

@@ -27,8 +27,13 @@ __global__ void __launch_bounds__(256) k_cell_keys(int m, const float *x, const 
 #pragma unroll
 	for (int d = 0; d < 3; ++d) {
 		long long v = (long long)floor(((double)p[d] - g.lo[d]) * g.inv[d]);
-		if (v < 0) v = 0;
-		if (v > g.nc[d] - 1) v = g.nc[d] - 1;
+		if (g.wrap[d]) { // a mover outside the box (input not pre-wrapped, a wrong -c) belongs to the periodic image of its cell
+			v %= g.nc[d];
+			if (v < 0) v += g.nc[d];
+		} else {
+			if (v < 0) v = 0;
+			if (v > g.nc[d] - 1) v = g.nc[d] - 1;
+		}
 		c[d] = v;
 	}
 	keys[i] = ((uint64_t)c[2] * (uint64_t)g.nc[1] + (uint64_t)c[1]) * (uint64_t)g.nc[0] + (uint64_t)c[0];

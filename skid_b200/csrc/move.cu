@@ -856,6 +856,17 @@ __global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *to
 	}
 }
 
+// ... and their fDensity reads as 0 afterwards, which kdOutStats' "gas mass" test sees (kd.c:1792-1794): a copy of
+// the densities by iOrder with the cut originals zeroed (only made when the input has gas, i.e. with -fic)
+__global__ void __launch_bounds__(256)
+    k_cut_density(int nEnt, const uint8_t *touched, const uint32_t *entSrc, const int *iordA, float *rhoStat)
+{
+	int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= nEnt || touched[e]) return;
+	const uint32_t src = entSrc[e];
+	if (!(src & 0x80000000u)) rhoStat[iordA[src]] = 0.0f;
+}
+
 // nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517).  Grid-stride over
 // [lo, hi) with one atomic per block (one per warp serialised 570 k same-address atomics per call).
 __global__ void __launch_bounds__(256) k_count_scatter(int lo, int hi, const float4 *entNR, const uint32_t *dT,
@@ -1031,7 +1042,10 @@ static const uint32_t *wait_log(skidgpu_ctx &c, int b)
 static void launch_tile_walk(skidgpu_ctx &c, const StepArgs &sa, const uint32_t *queue, const uint32_t *queueCount,
                              float reach, float reachShort, uint32_t *shortQueue, uint32_t *shortCount)
 {
-	SK_LAUNCH(k_tile_walk<8>, 148 * 8, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort, shortQueue, shortCount);
+	// (at most one warp per tile of the host's bound: small runs do not pay for 1184 idle blocks)
+	const unsigned want = (unsigned)ceil_div(ceil_div(c.nActiveBound > 0 ? c.nActiveBound : 1, TILE), 4);
+	SK_LAUNCH(k_tile_walk<8>, want < 148u * 8u ? want : 148u * 8u, 128, 0, c.stream, sa, queue, queueCount, reach, reachShort,
+	          shortQueue, shortCount);
 }
 
 // Sort the active movers by position and build the tile lists; valid for `steps` steps of length fStep.
@@ -1138,6 +1152,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	if (!c.rho.p) throw SkidError("skidgpu_move: skidgpu_density has not run");
 	StageTimer tm(c, 1);
 	c.bNoPrune = bNoPrune;
+	c.haveRhoStat = false;
 	for (int f : {KF_TILE_STEP, KF_BUILD, KF_FALLBACK, KF_PRUNE}) {
 		c.kernel_ms[f] = 0;
 		c.kernel_launches[f] = 0;
@@ -1228,6 +1243,12 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	if (bInitial && c.nEnt > 0) {
 		sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
 		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p);
+		if (c.nGas > 0) {
+			CK(cudaMemcpyAsync(c.rhoStat.alloc(n), c.rho.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+			SK_LAUNCH(k_cut_density, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entSrc.p, c.iordA.p,
+			          c.rhoStat.p);
+			c.haveRhoStat = true;
+		}
 	}
 	sa.touched = nullptr;
 	sa.a0x = sa.a0y = sa.a0z = nullptr;

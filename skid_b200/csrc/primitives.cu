@@ -85,10 +85,44 @@ static void scan_rec(const uint32_t *in, uint32_t *out, size_t n, DevBuf<uint32_
 	}
 }
 
+// Small inputs (the digit histograms of small sorts, the prune flags late in the move loop, the demo): one block
+// walks the whole array, tile by tile, carrying the running total - one launch instead of six.
+constexpr size_t SC_SMALL = 8 * SC_TILE; // 16384 elements (~12 us in one block; beyond that the multi-level scan wins)
+__global__ void __launch_bounds__(SC_THREADS) k_scan_small(const uint32_t *in, uint32_t *out, size_t n)
+{
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (size_t t0 = 0; t0 < n; t0 += SC_TILE) {
+		const size_t base = t0 + (size_t)threadIdx.x * SC_ITEMS;
+		uint32_t v[SC_ITEMS], tsum = 0;
+#pragma unroll
+		for (int i = 0; i < SC_ITEMS; ++i) {
+			v[i] = (base + i < n) ? in[base + i] : 0;
+			tsum += v[i];
+		}
+		uint32_t total;
+		uint32_t ex = block_exclusive_scan(tsum, &total) + carry;
+#pragma unroll
+		for (int i = 0; i < SC_ITEMS; ++i) {
+			if (base + i < n) out[base + i] = ex;
+			ex += v[i];
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) carry += total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[n] = carry;
+}
+
 void exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, Workspace &ws, cudaStream_t s)
 {
 	if (n == 0) {
 		CK(cudaMemsetAsync(out, 0, sizeof(uint32_t), s));
+		return;
+	}
+	if (n <= SC_SMALL) {
+		SK_LAUNCH(k_scan_small, 1, SC_THREADS, 0, s, in, out, n);
 		return;
 	}
 	DevBuf<uint32_t> *bufs[3] = {&ws.scanA, &ws.scanB, &ws.scanC};

@@ -232,7 +232,9 @@ void stage_stats(skidgpu_ctx &c, float fG, float z, double dExpHub, float fDensM
 	a.mass = c.mass.p;
 	a.soft = c.soft.p;
 	a.temp = c.temp.p;
-	a.rho = c.nAct > 0 ? c.rho.p : nullptr; // density stage did not run (-unbind restart): fDensity reads as 0
+	// density stage did not run (-unbind restart): fDensity reads as 0; after an initial cut (-fic) the cut
+	// scatterers read as 0 too (smooth1.c:463-470)
+	a.rho = c.nAct > 0 ? (c.haveRhoStat ? c.rhoStat.p : c.rho.p) : nullptr;
 	a.cat = c.gCat.p;
 	a.nGas = c.nGas;
 	a.nDark = c.nDark;

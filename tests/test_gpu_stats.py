@@ -113,3 +113,27 @@ def test_stat_file_vs_live_reference(tmp_path):
     if len(a) == len(b):
         same = np.isclose(a[:, 1:18], b[:, 1:18], rtol=2e-4, atol=1e-12).all(axis=1)
         assert same.mean() >= 0.95, same.mean()
+
+
+@pytest.mark.skipif(not refdump.have_ref(), reason="oracle/_ref not present")
+def test_stat_gas_mass_after_forced_initial_cut(tmp_path):
+    """-fic on a gas+dark input: smAccDensity(bInitial) zeroes fDensity of the scatterers that hit nobody
+    (smooth1.c:463-470), and kdOutStats' gas-mass column tests that fDensity (kd.c:1792-1794).  The gas-mass
+    column of host/skid -fic -stats must follow the live reference's."""
+    snap = synth.make_box(1 << 14, seed=11, kind="gasdark")
+    f = str(tmp_path / "in.std")
+    synth.write_std(snap, f)
+    args = snap["ref_args"] + ["-stats", "-fic"]
+    refdump.run_ref(f, args, str(tmp_path / "ref"))
+    with open(f, "rb") as fin:
+        r = subprocess.run([os.path.join(ROOT, "host", "skid")] + args + ["-o", str(tmp_path / "gpu")], stdin=fin,
+                           capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    a, b = np.loadtxt(str(tmp_path / "ref.stat"), ndmin=2), np.loadtxt(str(tmp_path / "gpu.stat"), ndmin=2)
+    assert abs(len(a) - len(b)) <= 1 and len(a) > 5
+    key = lambda t: np.lexsort((t[:, 14], t[:, 13], t[:, 12]))
+    a, b = a[key(a)], b[key(b)]
+    if len(a) == len(b):
+        same = np.isclose(a[:, 3], b[:, 3], rtol=2e-4, atol=1e-12)      # column 4 of the .stat: gas mass
+        assert same.mean() >= 0.95, same.mean()
+        assert a[:, 3].sum() > 0
