@@ -76,3 +76,10 @@ def test_massive_group_unbinding_config5():
     """The five largest FoF groups of the C5 box (2^24, tau x 4): 553 566 / 285 401 / 281 461 / 145 081 /
     144 725 members."""
     _run_case("C5")
+
+
+def test_massive_group_unbinding_config5_hot():
+    """The three largest groups of the C5 box with hotter halos (velocity dispersion x 1.8): 34 152, 17 484 and
+    17 462 removals from groups of 553 566 / 285 401 / 281 461 members - the removal loop itself (arg-max order,
+    rcm/vcm updates, kdSubPot after every removal) at full scale, through the thread-block-cluster kernel."""
+    _run_case("C5hot")
