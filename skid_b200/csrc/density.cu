@@ -78,6 +78,14 @@ __global__ void __launch_bounds__(256) k_gather_sortedA(int m, const uint32_t *p
 __device__ __forceinline__ uint64_t u64min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 __device__ __forceinline__ uint64_t u64max(uint64_t a, uint64_t b) { return a < b ? b : a; }
 
+// One compare-exchange of the networks below: this lane keeps the smaller (keepMin) or the larger of its value
+// and its partner's.  ONE 64-bit compare decides (ncu: the kernel is bound by the ALU pipe - ISETP/SEL - not by
+// issue slots, so the min-and-max-then-select form cost twice the compares).
+// (Comparing the keys as positive float64 - DSETP on the idle FP64 pipe - was measured: 99.3 -> 98.5 ms, the
+// register-pair moves eat the gain; the integer compare stays.)
+__device__ __forceinline__ bool key_lt(uint64_t a, uint64_t b) { return a < b; }
+__device__ __forceinline__ uint64_t cmpx(uint64_t v, uint64_t o, bool keepMin) { return (key_lt(v, o) == keepMin) ? v : o; }
+
 // ascending bitonic sort of one value per lane
 __device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane)
 {
@@ -85,10 +93,8 @@ __device__ __forceinline__ uint64_t warp_sort32(uint64_t v, int lane)
 	for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
 		for (int j = k >> 1; j > 0; j >>= 1) {
-			uint64_t o = __shfl_xor_sync(SK_FULL, v, j);
-			bool up = (lane & k) == 0;
-			bool lowhalf = (lane & j) == 0;
-			v = (lowhalf == up) ? u64min(v, o) : u64max(v, o);
+			const uint64_t o = __shfl_xor_sync(SK_FULL, v, j);
+			v = cmpx(v, o, ((lane & k) == 0) == ((lane & j) == 0));
 		}
 	}
 	return v;
@@ -98,8 +104,8 @@ __device__ __forceinline__ uint64_t warp_bitonic_merge32(uint64_t v, int lane)
 {
 #pragma unroll
 	for (int j = 16; j > 0; j >>= 1) {
-		uint64_t o = __shfl_xor_sync(SK_FULL, v, j);
-		v = (lane & j) ? u64max(v, o) : u64min(v, o);
+		const uint64_t o = __shfl_xor_sync(SK_FULL, v, j);
+		v = cmpx(v, o, (lane & j) == 0);
 	}
 	return v;
 }
@@ -119,7 +125,8 @@ template <int R> __device__ __forceinline__ void kbest_merge(uint64_t (&a)[R], u
 			return;
 		}
 		const uint64_t lr = __shfl_sync(SK_FULL, l, 31 - lane);
-		const uint64_t lo = u64min(a[r], lr), hi = u64max(a[r], lr);
+		const bool lt = key_lt(a[r], lr);
+		const uint64_t lo = lt ? a[r] : lr, hi = lt ? lr : a[r];
 		a[r + 1] = warp_bitonic_merge32(hi, lane);
 		l = warp_bitonic_merge32(lo, lane);
 	}
