@@ -775,6 +775,10 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 			sh.q[s] = q;
 		}
 		__syncthreads();
+		// (Measured and dropped: a two-phase chunk - hit bits first, then the hits of a mover pooled in a shared queue
+		// and dealt out evenly to its 8 lanes so that the spline block runs with all lanes.  ncu shows 21 of 32
+		// lanes active per instruction here, but the pooled hits are read back from random shared-memory slots
+		// (bank conflicts on the float4 records) and the kernel went from 168 to 313 ms per pass.)
 		if (run) {
 			for (int s = j; s < nc; s += LPM) {
 				const float4 p = sh.p[s];
