@@ -180,6 +180,8 @@ void dist_sort_pairs(skidgpu_ctx &c, uint64_t *keys, uint32_t *vals, size_t n, i
 #define SK_MAX 1
 #define SK_SUM 2
 
+constexpr int MOVE_OWN_BLOCK = 4096; // movers are owned in blocks of this many consecutive movers (move.cu)
+
 // stage entry points (each in its own .cu)
 void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, int *nExtraScat);
 void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, float fCvg, float fStep,

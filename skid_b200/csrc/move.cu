@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_iota(int lo, int cnt, uint32_t *out)
 // statistically identical sample.  The blocks are large (4096 Morton-consecutive movers = 128 supertiles):
 // with 256 every rank touched every scatterer of the box (the lists of neighbouring blocks overlap almost
 // completely), which cost the step kernel a third of its speed at 8 ranks.
-constexpr int OWN_BLOCK = 4096;
+constexpr int OWN_BLOCK = MOVE_OWN_BLOCK;
 __global__ void __launch_bounds__(256) k_owned_ids(int rank, int nranks, int own, uint32_t *out)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
