@@ -13,6 +13,7 @@
 // Scatterer pruning state of the reference is reproduced with two numbers per step:
 // T (entities with rho < T are gone) and the per-entity "cut at step 0" flag (rhoEff = 0).
 #include "ctx.cuh"
+#include <cuda_pipeline.h>
 #include <utility>
 
 #define T_NONE 0x7f800000u // +inf bits: "no entity was hit this step"
@@ -734,15 +735,19 @@ __device__ __forceinline__ void walk_one_mover(const StepArgs &a, const uint32_t
 // pair tests per tile are fixed (members x list length), so LPM lanes per mover instead of 32 keep the
 // lane work unchanged and divide the per-warp overhead by 32/LPM: one block of TILE*LPM threads per
 // tile, 32/LPM movers per warp.
-constexpr int TILE_CHUNK = 256; // records staged in shared memory at a time
+constexpr int TILE_CHUNK = 128; // records staged in shared memory at a time (two buffers)
 constexpr int LPM = 8;          // lanes per mover
 constexpr int TILE_THREADS = TILE * LPM;
 struct TileShared {
-	float4 p[TILE_CHUNK]; // (x,y,z,fBall2 or -1 when dead)
-	float4 q[TILE_CHUNK]; // (4/fBall2, fNorm, rho, 0)
+	float4 rec[2][TILE_CHUNK][2]; // the scatterer records as they lie in entRec: (x,y,z,fBall2), (4/fBall2, fNorm, rho, 0)
+	uint32_t e[2][TILE_CHUNK];    // their indices (only read at step 0, for the touched flags)
 };
 
-__device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, TileShared &sh, uint32_t *sh_e)
+// ncu on the synchronous version (profiles/r02_tilestep_2e24_*): issue active 68 %, 4.4 warps per issue slot waiting
+// on the long scoreboard - the chain list index -> record gather -> shared store of the staging loop.  The records
+// now travel with asynchronous copies (cp.async, 16 bytes each, LDGSTS in SASS) into one of two buffers while the
+// previous chunk is being evaluated; the list indices of the chunk after that are already in registers.
+__device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, TileShared &sh)
 {
 	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
 	const int cnt = a.tCnt[t];
@@ -762,36 +767,52 @@ __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, T
 	const uint32_t *list = a.tList + a.tOff[t];
 	float ax = 0.0f, ay = 0.0f, az = 0.0f;
 	float rmin = 3.0e38f;
-	for (int c0 = 0; c0 < cnt; c0 += TILE_CHUNK) {
-		const int nc = min(cnt - c0, TILE_CHUNK);
-		if (c0) __syncthreads();
-		for (int s = threadIdx.x; s < nc; s += TILE_THREADS) {
-			const uint32_t e = list[c0 + s];
-			float4 p = a.entRec[2 * (size_t)e];
-			const float4 q = a.entRec[2 * (size_t)e + 1];
-			if (!(q.z >= T)) p.w = -1.0f; // pruned since the list was built
-			if (a.touched) sh_e[s] = e;
-			sh.p[s] = p;
-			sh.q[s] = q;
+	constexpr int PER = TILE_CHUNK / TILE_THREADS; // records per thread and chunk
+	const int nch = cnt > 0 ? (cnt + TILE_CHUNK - 1) / TILE_CHUNK : 0;
+	uint32_t en[PER]; // list entries of the next chunk to be issued
+#pragma unroll
+	for (int k = 0; k < PER; ++k) en[k] = (int)threadIdx.x + k * TILE_THREADS < cnt ? list[threadIdx.x + k * TILE_THREADS] : 0u;
+	auto issue = [&](int ci) { // start the copies of chunk ci (its indices are in en[]), fetch the indices of chunk ci + 1
+		const int c0 = ci * TILE_CHUNK, bsel = ci & 1;
+#pragma unroll
+		for (int k = 0; k < PER; ++k) {
+			const int s = (int)threadIdx.x + k * TILE_THREADS;
+			if (c0 + s < cnt) {
+				const float4 *src = a.entRec + 2 * (size_t)en[k];
+				__pipeline_memcpy_async(&sh.rec[bsel][s][0], src, 16);
+				__pipeline_memcpy_async(&sh.rec[bsel][s][1], src + 1, 16);
+				if (a.touched) sh.e[bsel][s] = en[k];
+			}
+			const int nx = c0 + TILE_CHUNK + s;
+			en[k] = nx < cnt ? list[nx] : 0u;
 		}
-		__syncthreads();
-		// (Measured and dropped: a two-phase chunk - hit bits first, then the hits of a mover pooled in a shared queue
-		// and dealt out evenly to its 8 lanes so that the spline block runs with all lanes.  ncu shows 21 of 32
-		// lanes active per instruction here, but the pooled hits are read back from random shared-memory slots
-		// (bank conflicts on the float4 records) and the kernel went from 168 to 313 ms per pass.)
+		__pipeline_commit();
+	};
+	if (nch > 0) issue(0);
+	for (int ci = 0; ci < nch; ++ci) {
+		const int bsel = ci & 1;
+		const int nc = min(cnt - ci * TILE_CHUNK, TILE_CHUNK);
+		if (ci + 1 < nch) {
+			issue(ci + 1);
+			__pipeline_wait_prior(1);
+		} else __pipeline_wait_prior(0);
+		__syncthreads(); // every thread's copies of chunk ci have landed
 		if (run) {
 			for (int s = j; s < nc; s += LPM) {
-				const float4 p = sh.p[s];
+				const float4 p = sh.rec[bsel][s][0];
 				// smBallGather (smooth1.c:365-369): dx = x_scatterer - x_mover, float32, no FMA
 				const float dx = __fsub_rn(p.x, x), dy = __fsub_rn(p.y, y), dz = __fsub_rn(p.z, z);
 				const float d2 = dist2_rn(dx, dy, dz);
 				if (d2 < p.w) {
-					const float4 q = sh.q[s];
-					ACC_HIT(dx, dy, dz, d2, q);
-					if (a.touched) a.touched[sh_e[s]] = 1;
+					const float4 q = sh.rec[bsel][s][1];
+					if (q.z >= T) { // not pruned since the list was built
+						ACC_HIT(dx, dy, dz, d2, q);
+						if (a.touched) a.touched[sh.e[bsel][s]] = 1;
+					}
 				}
 			}
 		}
+		__syncthreads(); // the buffer is free for chunk ci + 2
 	}
 #pragma unroll
 	for (int o = LPM / 2; o > 0; o >>= 1) {
@@ -833,10 +854,9 @@ __global__ void k_update_T(uint32_t *dT, int bNoPrune, int par, int launched) { 
 // blocks more than the launch it saves: k_tile_step 164 -> 175 ms per pass.)
 __global__ void __launch_bounds__(TILE_THREADS) k_tile_step(const StepArgs a)
 {
-	__shared__ TileShared sh;
-	__shared__ uint32_t sh_e[TILE_CHUNK];
+	__shared__ __align__(16) TileShared sh;
 	const int t = blockIdx.x;
-	if (t * TILE < N_ACTIVE(a)) tile_step_body(a, t, sh, sh_e);
+	if (t * TILE < N_ACTIVE(a)) tile_step_body(a, t, sh);
 }
 
 // Test hook (skidgpu_debug_move_kernel): every active mover takes the step with its own tree walk.

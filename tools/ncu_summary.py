@@ -10,7 +10,9 @@ WANT = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
-    "lts__t_bytes.sum": "l2_bytes", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "lts__t_sectors.sum": "l2_sectors", "lts__t_sector_hit_rate.pct": "l2_hit_pct",
+    "lts__t_sectors.sum.pct_of_peak_sustained_elapsed": "l2_sector_throughput_pct",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "l1_global_load_sectors",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
     "l1tex__t_sector_hit_rate.pct": "l1_hit_pct", "l1tex__throughput.avg.pct_of_peak_sustained_active": "l1_throughput_pct",
     "launch__registers_per_thread": "regs", "launch__grid_size": "grid", "launch__block_size": "block",
@@ -34,6 +36,10 @@ for k, r in enumerate(rows[2:]):
             v = float(r[i].replace(",", ""))
             v *= UNIT.get(units[i], 1.0)
             out[WANT[c]] = v
+    if "l2_sectors" in out:
+        out["l2_bytes"] = 32.0 * out["l2_sectors"]
+    if "l1_global_load_sectors" in out:
+        out["l1_global_load_bytes"] = 32.0 * out["l1_global_load_sectors"]
     if k < len(div):
         u = div[k]
         out["units"] = u
