@@ -26,6 +26,8 @@ def lib():
         L.orc_replicas.restype = i
         L.orc_gradient.argtypes = [i, vp, vp, vp, vp, vp, i, vp, vp, vp]
         L.orc_gradient.restype = f
+        L.orc_gradient_abs.argtypes = [i, vp, vp, vp, i, vp, vp]
+        L.orc_gradient_abs.restype = None
         L.orc_move_loop.argtypes = [i, vp, vp, vp, vp, i, vp, f, vp, f, f, i, i, i, vp, vp, i, f, vp]
         L.orc_move_loop.restype = i
         L.orc_fof.argtypes = [i, vp, f, f, vp]
@@ -75,6 +77,14 @@ def gradient(epos, eball2, emass, erho, mpos, alive=None):
     al = None if alive is None else np.ascontiguousarray(alive, np.uint8)
     fsd = lib().orc_gradient(ne, _p(epos), _p(eball2), _p(emass), _p(erho), _p(al), nm, _p(mpos), _p(acc), _p(touched))
     return acc, touched, float(fsd)
+
+
+def gradient_abs(epos, eball2, emass, mpos):
+    """Per mover, the sum of the magnitudes of its gradient terms (the scale of the float32 summation noise)."""
+    epos, eball2, emass, mpos = map(_f32, (epos, eball2, emass, mpos))
+    sabs = np.empty(len(mpos), np.float64)
+    lib().orc_gradient_abs(len(epos), _p(epos), _p(eball2), _p(emass), len(mpos), _p(mpos), _p(sabs))
+    return sabs
 
 
 def move_loop(epos, eball2, emass, erho, mpos, period, center, fCvg, fStep, bInitial, bNoPrune=False, nMicro=5,

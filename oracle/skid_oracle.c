@@ -193,6 +193,23 @@ float orc_gradient(int nEnt, const float *epos, const float *eball2, const float
 	return fScatDens;
 }
 
+/* Sum over the hits of a mover of the MAGNITUDES of the gradient terms, S_m = sum |x_e - x_m| |w| : the scale
+ * against which the float32 summation noise of smAccDensity (smooth1.c:447-459) is judged - SURVEY 8c:
+ * |a_gpu - a_ref| <= 1e-5 S_m, where |a| itself can be arbitrarily small by cancellation. */
+void orc_gradient_abs(int nEnt, const float *epos, const float *eball2, const float *emass, int nMove,
+                      const float *mpos, double *sabs)
+{
+	int e, m;
+	for (m = 0; m < nMove; ++m) sabs[m] = 0.0;
+	for (e = 0; e < nEnt; ++e)
+		for (m = 0; m < nMove; ++m) {
+			float dx = epos[3 * e] - mpos[3 * m], dy = epos[3 * e + 1] - mpos[3 * m + 1],
+			      dz = epos[3 * e + 2] - mpos[3 * m + 2];
+			float d2 = dist2f(dx, dy, dz);
+			if (d2 < eball2[e]) sabs[m] += sqrt((double)d2) * fabs((double)grad_weight(d2, eball2[e], emass[e]));
+		}
+}
+
 /* ---- the flow loop: scatter form over a uniform grid of the ACTIVE movers ------------------- */
 
 typedef struct {

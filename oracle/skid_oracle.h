@@ -39,6 +39,8 @@ int orc_replicas(int n, const float *pos, const float *ball2, float period, cons
  * |x_e - x_m|^2 < ball2_e (float32, non-periodic): a_m += (x_e-x_m)*g(q)*fNorm_e.
  * ent_alive[e] != 0 marks active entities.  touched[e] is set for entities with >= 1 hit.
  * Returns fScatDens = min rho over touched entities (0 if none). */
+void orc_gradient_abs(int nEnt, const float *epos, const float *eball2, const float *emass, int nMove,
+                      const float *mpos, double *sabs);
 float orc_gradient(int nEnt, const float *epos, const float *eball2, const float *emass, const float *erho,
                    const unsigned char *ent_alive, int nMove, const float *mpos, float *acc,
                    unsigned char *touched);

@@ -47,9 +47,10 @@ def compare_group_table(gold, grp, cat_mass):
 
 
 def compare(gold, grp, nIttr, nGroupBefore, nUnbound, nGroup, cat_mass=None):
-    """north_star tolerances for the synthetic boxes: >= 99.9 % of the particles in the same group; the counters
-    of the run agree with the reference's to a fraction of a per cent (they are identical on every box up to
-    2^18, but a single mover converging one block later may shift them)."""
+    """north_star tolerances for the synthetic boxes: >= 99.9 % of the particles in the same group.  The counters:
+    iteration and group counts as before; "particles Unbound" within 1e-4 relative - the removals that differ are
+    those of small loosely bound groups whose members sit at E ~ 0 in float32 (kd.c:1398) and which kdTooSmall
+    deletes afterwards in both codes (observed: +2 of 567 192, +4 of 3 311 497, +87 of 4 043 809)."""
     gI, gB, gU, gG, _ = [int(v) for v in gold["log"]]
     stride = int(gold["stride"])
     same = float(np.mean(canonical_min_member(grp)[::stride] == gold["sample_canon"]))
@@ -61,8 +62,8 @@ def compare(gold, grp, nIttr, nGroupBefore, nUnbound, nGroup, cat_mass=None):
     assert abs(nIttr - gI) <= 2, report
     assert abs(nGroupBefore - gB) <= max(1, gB // 1000), report
     assert abs(nGroup - gG) <= max(1, gG // 1000), report
-    assert abs(nUnbound - gU) <= max(2, gU // 100), report
-    assert np.all(np.abs(sizes[:k].astype(np.int64) - gold["sizes"][:k]) <= np.maximum(2, gold["sizes"][:k] // 100)), report
+    assert abs(nUnbound - gU) <= max(8, gU // 10000), report
+    assert np.all(np.abs(sizes[:k].astype(np.int64) - gold["sizes"][:k]) <= np.maximum(2, gold["sizes"][:k] // 1000)), report
     if cat_mass is not None:
         report["masses"] = compare_group_table(gold, grp, cat_mass)
         if report["masses"] is not None:

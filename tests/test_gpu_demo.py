@@ -112,7 +112,7 @@ def test_replicas_and_log(demo_run, demo_golden):
     assert len(micro) == 5
 
 
-def test_step0_gradient_and_initial_cut(demo_run, demo_golden):
+def test_step0_gradient_and_initial_cut(demo_run, demo_golden, demo_input):
     iord, a, alive = demo_run["step0"]
     ref_a = np.zeros((len(demo_golden["ball2"]), 3), np.float64)
     ref_a[demo_golden["step0_iOrder"]] = demo_golden["step0_a"]
@@ -121,9 +121,18 @@ def test_step0_gradient_and_initial_cut(demo_run, demo_golden):
     assert sorted(iord.tolist()) == sorted(demo_golden["step0_iOrder"].tolist())
     da = np.linalg.norm(mine - ref_a, axis=1)[iord]
     na = np.linalg.norm(ref_a, axis=1)[iord]
-    # max |da|/|a| = 1.02e-5 between gather and scatter form (cancellation); f32 order noise
-    assert np.percentile(da / na, 99) < 2e-5
-    assert (da / na).max() < 5e-4
+    # the difference is float32 summation order (gather form here, scatter form in the reference), so it
+    # is bounded by the summed MAGNITUDES of a mover's terms, not by |a| (which cancels): |da| <= 1e-5 sum|terms|
+    from oracle import orc
+    p = demo_input[0]
+    src, rp = orc.replicas(p["r"], demo_golden["ball2"], 1.0)
+    eidx = np.concatenate([np.arange(len(p)), src])
+    sabs = orc.gradient_abs(np.concatenate([p["r"], rp]), demo_golden["ball2"][eidx], p["fMass"][eidx], p["r"][iord])
+    rel = da / na
+    print("step-0 gradient |da|/|a| percentiles 50/90/99/99.9/max:",
+          [float("%.3g" % v) for v in np.percentile(rel, [50, 90, 99, 99.9, 100])], "max |da|/sum|terms|: %.3g" % (da / sabs).max())
+    assert np.all(da <= 1e-5 * sabs), float((da / sabs).max())
+    assert np.percentile(rel, 99) < 1e-5
     # survivors of the initial cut: exact set of originals (20 409 on the demo)
     ref_alive = np.unpackbits(demo_golden["step0_alive"])[: len(alive)]
     assert np.array_equal(alive, ref_alive)
