@@ -642,12 +642,13 @@ void stage_density(skidgpu_ctx &c, int nSmooth, int bGasAndDark, int bGasOnly, i
 	float4 *enr = c.entNR.alloc(ne + 64);
 	uint32_t *esrc = c.entSrc.alloc(ne);
 	float *inflS = c.tmpx.alloc(ne);
-	float *rhoS = c.eRhoSorted.alloc(ne);
+	float *rhoS = c.eRhoSorted.alloc((size_t)ne + 64); // compact copy of rhoEff: read beside the positions by the list walks
 	float4 *erec = c.entRec.alloc(2 * ((size_t)ne + 64));
 	SK_LAUNCH(k_gather_entities, (unsigned)ceil_div(ne, 256), 256, 0, s, ne, c.treeE.perm.p, posU, nrU, srcU, einfl, ep,
 	          enr, esrc, inflS, rhoS, erec);
 	// pad the sorted scatterer arrays to whole leaves with dummies that can never be hit (fBall2 = -1)
 	SK_LAUNCH(k_pad_entities, 1, 64, 0, s, ne, ep, enr);
+	CK(cudaMemsetAsync(rhoS + ne, 0, sizeof(float) * 64, s));
 	tree_build_boxes(c.treeE, ep, inflS, rhoS, ne, s, 32, 32);
 	CK(cudaMemsetAsync(c.entTouched.alloc(ne + 64), 0, ne + 64, s));
 	tm.stop();

@@ -178,6 +178,7 @@ struct StepArgs {
 	TreeView tv;
 	const float4 *entPos; // (x,y,z,fBall2)
 	const float4 *entNR;  // (4/fBall2, fNorm, rhoEff, 0)
+	const float *entRho;  // rhoEff alone (the list walks read it beside entPos)
 	const float4 *entRec; // the two interleaved: rec[2e] = entPos[e], rec[2e+1] = entNR[e] (list path gathers)
 	uint8_t *touched;     // nullable: set for entities with >= 1 hit (step 0, initial cut)
 	float *mx, *my, *mz;
@@ -488,9 +489,10 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 				}
 				const uint32_t e = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
 				const float4 p = a.entPos[e];
+				const float rho = a.entRho[e];
 				bool cand;
 				TILE_MEMBER_TEST(p, cand);
-				if (cand) cand = a.entNR[e].z >= T; // dead scatterers never come back
+				cand = cand && rho >= T; // dead scatterers never come back
 				TILE_APPEND(cand, e);
 			}
 #undef TILE_TEST_CHILDREN
@@ -563,13 +565,13 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, float reac
 		if (lane == lev) mymask = m_;                                                          \
 	}
 	// superset candidate <=> dist(x_e, box) <= h + r (same algebra as the member test)
-#define SUPER_LEAF(e_, p)                                                                              \
+#define SUPER_LEAF(e_, p, rho_)                                                                            \
 	{                                                                                              \
 		const float gx = fmaxf(fmaxf(x0 - (p).x, (p).x - x1), 0.0f), gy = fmaxf(fmaxf(y0 - (p).y, (p).y - y1), 0.0f), \
 		            gz = fmaxf(fmaxf(z0 - (p).z, (p).z - z1), 0.0f);                           \
 		const float u_ = gx * gx + gy * gy + gz * gz - (p).w - r2;                             \
 		bool cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);           \
-		if (cand) cand = a.entNR[e_].z >= T; /* dead scatterers never come back */             \
+		cand = cand && (rho_) >= T; /* dead scatterers never come back */                      \
 		const uint32_t cm = __ballot_sync(SK_FULL, cand);                                      \
 		const int nc = __popc(cm);                                                             \
 		if (ns + nc > a.supCap) overflow = true;                                               \
@@ -597,17 +599,19 @@ __global__ void __launch_bounds__(128) k_super_walk(const StepArgs a, float reac
 		// leaf level: two buckets per round so that two record loads are in flight
 		const uint32_t e0 = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
 		const float4 p0 = a.entPos[e0];
+		const float rho0 = a.entRho[e0]; // (a 4-byte coalesced row beside the positions, not a gather behind the test)
 		if (mk) {
 			const int c1 = __ffs(mk) - 1;
 			mk &= mk - 1;
 			const uint32_t e1 = (node * 32 + c1) * 32 + lane;
 			const float4 p1 = a.entPos[e1];
+			const float rho1 = a.entRho[e1];
 			if (lane == 0) mymask = mk;
-			SUPER_LEAF(e0, p0);
-			SUPER_LEAF(e1, p1);
+			SUPER_LEAF(e0, p0, rho0);
+			SUPER_LEAF(e1, p1, rho1);
 		} else {
 			if (lane == 0) mymask = mk;
-			SUPER_LEAF(e0, p0);
+			SUPER_LEAF(e0, p0, rho0);
 		}
 	}
 #undef SUPER_TEST_CHILDREN
@@ -872,12 +876,13 @@ __global__ void __launch_bounds__(STEP_WARPS * 32) k_move_step(const StepArgs a,
 }
 
 // Initial cut (smooth1.c:463-470,500-507): entities that scattered onto nobody get fDensity = 0.
-__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float4 *entNR, float4 *entRec)
+__global__ void __launch_bounds__(256) k_initial_cut(int nEnt, const uint8_t *touched, float4 *entNR, float4 *entRec, float *entRho)
 {
 	int e = blockIdx.x * blockDim.x + threadIdx.x;
 	if (e < nEnt && !touched[e]) {
 		entNR[e].z = 0.0f;
 		entRec[2 * (size_t)e + 1].z = 0.0f;
+		entRho[e] = 0.0f;
 	}
 }
 
@@ -979,6 +984,7 @@ static void fill_step_args(skidgpu_ctx &c, StepArgs &sa, float fStep)
 	sa.tv = tree_view(c.treeE);
 	sa.entPos = c.entPos.p;
 	sa.entNR = c.entNR.p;
+	sa.entRho = c.eRhoSorted.p;
 	sa.entRec = c.entRec.p;
 	sa.touched = nullptr;
 	sa.mx = c.mx.p;
@@ -1267,7 +1273,8 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 	c.tileWindow = 5;
 	if (bInitial && c.nEnt > 0) {
 		sk_reduce(c, c.entTouched.p, c.nEnt, SK_U8, SK_MAX);
-		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p);
+		SK_LAUNCH(k_initial_cut, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entNR.p, c.entRec.p,
+		          c.eRhoSorted.p);
 		if (c.nGas > 0) {
 			CK(cudaMemcpyAsync(c.rhoStat.alloc(n), c.rho.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToDevice, s));
 			SK_LAUNCH(k_cut_density, (unsigned)ceil_div(c.nEnt, 256), 256, 0, s, c.nEnt, c.entTouched.p, c.entSrc.p, c.iordA.p,
