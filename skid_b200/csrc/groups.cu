@@ -394,7 +394,8 @@ template <int MODE> __global__ void __launch_bounds__(256) k_scoop(const ScoopAr
 // off-diagonal tile is swept by rotation (thread i meets column (i + t) mod POT_T at step t), the row terms go
 // to a register and the column terms to a per-warp shared array, so no two lanes touch the same column at the
 // same step.  Per-pair arithmetic is the reference's (float32 geometry, dir, float32 product G*m*dir, float64
-// sums); a tile's partial sums reach the float64 potential with one atomic per member.
+// sums); a tile's partial sums reach the float64 potential with one atomic per member.  (Storing the tile twice in a
+// row so that the rotation index never wraps - no index arithmetic in the loop - was measured: no gain, 447 -> 462 ms.)
 // ncu on the massive-halo box (config 5, profiles/r02_*): the two-sided loop that evaluated every pair twice was
 // 523 ms of a 1025 ms pass (5.4e11 warp instructions, issue bound).
 constexpr int POT_T = 128;
