@@ -223,18 +223,26 @@ void stage_set_groups(skidgpu_ctx &c, const int *piGroup, int nGroup, const skid
 // =====================================================================================
 // unbinding
 // =====================================================================================
-__global__ void __launch_bounds__(256) k_gid_keys(int n, const int *gid, uint64_t *keys, uint32_t *vals)
+// grouped / ungrouped flags and their compaction (ascending iOrder): only the grouped particles are sorted by label
+__global__ void __launch_bounds__(256) k_label_flags(int n, const int *gid, int wantGrouped, uint32_t *flags)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	keys[i] = (uint64_t)(uint32_t)gid[i];
-	vals[i] = (uint32_t)i;
+	if (i < n) flags[i] = ((gid[i] > 0) == (wantGrouped != 0)) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256)
+    k_label_compact(int n, const int *gid, const uint32_t *flags, const uint32_t *scan, uint64_t *keys, uint32_t *idx)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !flags[i]) return;
+	const uint32_t k = scan[i];
+	if (keys) keys[k] = (uint64_t)(uint32_t)gid[i];
+	idx[k] = (uint32_t)i;
 }
 
 // group-ordered member arrays: relative coordinates (kd.c:1341-1355)
 struct MemArgs {
 	int n, n0;
-	const uint32_t *order; // sorted by group: file indices
+	const uint32_t *order; // the grouped particles sorted by group: file indices
 	const int *gid;
 	const skidgpu_pgroup *cat;
 	const float *x, *y, *z, *vx, *vy, *vz, *mass, *soft;
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(256) k_members(const MemArgs a)
 {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= a.n - a.n0) return;
-	uint32_t i = a.order[a.n0 + k];
+	uint32_t i = a.order[k];
 	int g = a.gid[i];
 	if (g % a.nranks != a.rank) return; // only the owner of a group reads its members (potentials, removal loop)
 	const float *rel = a.cat[g].rel;
@@ -325,6 +333,8 @@ struct ScoopArgs {
 	const uint32_t *start;
 	uint32_t *list;
 	int rank, nranks;
+	const int *iord; // non-null: the tree holds ALL particles (the kNN tree); sources are those with label 0
+	const int *gid;
 };
 
 template <int MODE> __global__ void __launch_bounds__(256) k_scoop(const ScoopArgs a)
@@ -378,6 +388,7 @@ template <int MODE> __global__ void __launch_bounds__(256) k_scoop(const ScoopAr
 				float d2 = dist2_rn(minimg_dx(x0, xp, xm, a.hL[0], p.x), minimg_dx(y0, yp, ym, a.hL[1], p.y),
 				                    minimg_dx(z0, zp, zm, a.hL[2], p.z));
 				hit = d2 < a.fBall2; // grav.c:102
+				if (hit && a.iord) hit = a.gid[a.iord[idx]] == 0;
 			}
 			uint32_t hm = __ballot_sync(SK_FULL, hit);
 			if (MODE && hit) a.list[outBase + count + __popc(hm & lt)] = (uint32_t)idx;
@@ -413,8 +424,10 @@ struct PotArgs {
 	// scoop
 	const uint32_t *scStart; // [nGroup+1]
 	const uint32_t *scList;
-	const float4 *posS;      // (x,y,z,mass) sorted ungrouped
-	const float *softS;
+	const float4 *posS;      // (x,y,z,mass) of the scoop tree's points
+	const float *softS;      // their softening, or ...
+	const int *srcIdx;       // ... non-null: softening = soft[srcIdx[point]] (scoop from the kNN tree)
+	const float *soft;
 	const skidgpu_pgroup *cat;
 	float L[3];
 	float G;
@@ -523,7 +536,7 @@ __global__ void __launch_bounds__(POT_T) k_group_pot(const PotArgs a)
 			nx = wrap_del(nx, a.L[0]);
 			ny = wrap_del(ny, a.L[1]);
 			nz = wrap_del(nz, a.L[2]);
-			s_r[tid] = make_float4(nx, ny, nz, a.softS[sidx]);
+			s_r[tid] = make_float4(nx, ny, nz, a.srcIdx ? a.soft[a.srcIdx[sidx]] : a.softS[sidx]);
 			s_m[tid] = __fmul_rn(a.G, p.w);
 		}
 		__syncthreads();
@@ -1215,15 +1228,11 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 	unsigned int hUnbound = 0;
 
 	if (G > 1) {
-		// ---- kdGroupOrder: members of each group contiguous, group 0 first
-		keys.alloc(n);
-		order.alloc(n);
-		SK_LAUNCH(k_gid_keys, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, keys.p, order.p);
-		int bits = 1;
-		while ((1ll << bits) < (long long)G) ++bits;
-		dist_sort_pairs(c, keys.p, order.p, n, bits); // replicated input: shared between the ranks
+		// ---- kdGroupOrder: members of each group contiguous.  Only the grouped particles are sorted (by label,
+		// stable: ascending iOrder within a group); most particles are ungrouped and keep their order.
 		cntU.alloc(G + 2);
 		uint32_t *scan = c.scan.alloc((size_t)(G > n ? G : n) + 64);
+		uint32_t *flags = c.flags.alloc((size_t)n + 1);
 		SK_LAUNCH(k_copy_counts, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, cntU.p);
 		exclusive_scan_u32(cntU.p, scan, G, c.ws, s);
 		int n0 = 0;
@@ -1232,25 +1241,48 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 		gStart.alloc(G + 2);
 		SK_LAUNCH(k_gstart_rel, (unsigned)ceil_div(G + 1, 256), 256, 0, s, G, scan, n0, gStart.p);
 		const int nm = n - n0; // grouped particles
+		keys.alloc(nm > 0 ? nm : 1);
+		order.alloc(nm > 0 ? nm : 1);
+		if (nm > 0) {
+			SK_LAUNCH(k_label_flags, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, 1, flags);
+			exclusive_scan_u32(flags, scan, n, c.ws, s);
+			SK_LAUNCH(k_label_compact, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, flags, scan, keys.p, order.p);
+			int bits = 1;
+			while ((1ll << bits) < (long long)G) ++bits;
+			dist_sort_pairs(c, keys.p, order.p, nm, bits); // replicated input: shared between the ranks
+		}
 
-		// ---- tree over the ungrouped particles for the scoop (kd.c:1324-1325)
-		posS.alloc(n0 > 0 ? n0 : 1);
-		softS.alloc(n0 > 0 ? n0 : 1);
-		if (n0 > 0) {
+		// ---- the scoop sources (kd.c:1324-1325: a tree over the ungrouped particles).  When the kNN tree of the
+		// density stage holds every particle (dark-only inputs, -gd) it serves as it is, with the label test at
+		// the leaves; otherwise (other species mixes, the -unbind restart) a tree over the ungrouped is built.
+		const bool reuseA = c.nAct == n && c.treeA.n == n && c.posA.p && c.iordA.p;
+		if (!reuseA) {
+			posS.alloc(n0 > 0 ? n0 : 1);
+			softS.alloc(n0 > 0 ? n0 : 1);
+		}
+		if (!reuseA && n0 > 0) {
+			DevBuf<uint32_t> idx0;
+			idx0.alloc(n0);
 			sx.alloc(n0);
 			sy.alloc(n0);
 			sz.alloc(n0);
-			SK_LAUNCH(k_gather_scoop_src, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, order.p, c.x.p, c.y.p, c.z.p, sx.p,
+			SK_LAUNCH(k_label_flags, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, 0, flags);
+			exclusive_scan_u32(flags, scan, n, c.ws, s);
+			SK_LAUNCH(k_label_compact, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, flags, scan, (uint64_t *)nullptr, idx0.p);
+			SK_LAUNCH(k_gather_scoop_src, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, idx0.p, c.x.p, c.y.p, c.z.p, sx.p,
 			          sy.p, sz.p);
 			tree_sort_points(treeS, sx.p, sy.p, sz.p, n0, c.ws, s, nullptr, &c);
-			SK_LAUNCH(k_gather_scoop_sorted, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, treeS.perm.p, order.p, c.x.p,
+			SK_LAUNCH(k_gather_scoop_sorted, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, treeS.perm.p, idx0.p, c.x.p,
 			          c.y.p, c.z.p, c.mass.p, c.soft.p, posS.p, softS.p);
 			tree_build_boxes(treeS, posS.p, nullptr, nullptr, n0, s);
+			CK(cudaStreamSynchronize(s)); // idx0 goes out of scope
 		}
 		ScoopArgs sc;
-		sc.tv = tree_view(treeS);
-		sc.posS = posS.p;
-		sc.nS = n0;
+		sc.tv = tree_view(reuseA ? c.treeA : treeS);
+		sc.posS = reuseA ? c.posA.p : posS.p;
+		sc.nS = reuseA ? n : n0;
+		sc.iord = reuseA ? c.iordA.p : nullptr;
+		sc.gid = c.gid.p;
 		sc.nGroup = G;
 		sc.cat = c.gCat.p;
 		for (int d = 0; d < 3; ++d) {
@@ -1328,8 +1360,10 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			pa.pot = pot.p;
 			pa.scStart = scStart.p;
 			pa.scList = scList.p;
-			pa.posS = posS.p;
+			pa.posS = reuseA ? c.posA.p : posS.p;
 			pa.softS = softS.p;
+			pa.srcIdx = reuseA ? c.iordA.p : nullptr;
+			pa.soft = c.soft.p;
 			pa.cat = c.gCat.p;
 			for (int d = 0; d < 3; ++d) pa.L[d] = c.L[d];
 			pa.G = fG;
