@@ -255,6 +255,15 @@ def main():
     host_aos = pin.numpy().view(PINIT_DTYPE)
     host_aos[:] = p
     del p
+    # pinned result buffers of the e2e leg (labels by iOrder, catalogue rows)
+    from skid_b200.tipsy import PGROUP_DTYPE
+    try:
+        pin_grp = torch.empty(n, dtype=torch.int32).pin_memory()
+        pin_cat = torch.empty((n // 16 + 1024) * PGROUP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    except Exception:
+        pin_grp = torch.empty(n, dtype=torch.int32)
+        pin_cat = torch.empty((n // 16 + 1024) * PGROUP_DTYPE.itemsize, dtype=torch.uint8)
+    out_grp, out_cat = pin_grp.numpy(), pin_cat.numpy().view(PGROUP_DTYPE)
     torch.cuda.synchronize()
 
     per = (fl["period"],) * 3
@@ -277,7 +286,8 @@ def main():
         fetch = host and rank == 0 if shard else host
         if shard:
             return parallel.run_skid_sharded(sk, reducer, host_aos, snap["nGas"], snap["nDark"], snap["nStar"], fl,
-                                             rank, world, host=host, dev_ptrs=[t.data_ptr() for t in dev], fetch=fetch)
+                                             rank, world, host=host, dev_ptrs=[t.data_ptr() for t in dev], fetch=fetch,
+                                             out_grp=out_grp, out_cat=out_cat)
         sk.log = []
         if host:
             sk.set_particles(host_aos, snap["nGas"], snap["nDark"], snap["nStar"])
@@ -288,7 +298,8 @@ def main():
         sk.kdFoF(tau)
         sk.microstep(5, f32(0.1 * fStep))
         sk.kdCalcCenter(fetch=False)
-        return sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX, fl["nMembers"], fetch=fetch)
+        return sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, api.INT_MAX, fl["nMembers"], fetch=fetch,
+                           out_grp=out_grp, out_cat=out_cat)
 
     stream = torch.cuda.ExternalStream(sk.stream(), device=torch.device("cuda", local))
 

@@ -262,10 +262,13 @@ class SkidGPU:
         self._ck(self.lib.skidgpu_set_groups(self.h, _ptr(piGroup), nGroup, _ptr(centres)))
 
     def kdUnbind(self, G=1.0, z=0.0, fCosmo=0.0, iSoftType=SPLINE, fScoop=0.0, bNoUnbind=False, nMaxMembers=INT_MAX,
-                 nMinMembers=8, fetch=True):
-        """fetch=False leaves labels and catalogue on the device (returned as None): counters only."""
-        grp = np.empty(self.n, np.int32) if fetch else None
-        cat = np.zeros(max(self.nGroup, 1), PGROUP_DTYPE) if fetch else None
+                 nMinMembers=8, fetch=True, out_grp=None, out_cat=None):
+        """fetch=False leaves labels and catalogue on the device (returned as None): counters only.
+        out_grp / out_cat: caller-owned result arrays (e.g. pinned host memory) of at least n / nGroup entries."""
+        grp = cat = None
+        if fetch:
+            grp = np.empty(self.n, np.int32) if out_grp is None else out_grp[:self.n]
+            cat = np.zeros(max(self.nGroup, 1), PGROUP_DTYPE) if out_cat is None else out_cat[:max(self.nGroup, 1)]
         ng, nu, nb = C.c_int(0), C.c_int(0), C.c_int(0)
         self._ck(self.lib.skidgpu_unbind(self.h, G, z, fCosmo, iSoftType, fScoop, int(bNoUnbind), nMaxMembers,
                                          nMinMembers, _ptr(grp), _ptr(cat), C.byref(ng), C.byref(nu), C.byref(nb)))

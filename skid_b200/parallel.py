@@ -198,7 +198,7 @@ class _nullcontext:
 
 
 def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks, host=True, dev_ptrs=None,
-                     fetch=True):
+                     fetch=True, out_grp=None, out_cat=None):
     """The main.c stage script on a sharded snapshot.  sk: api.SkidGPU with comm_init (or set_shard + reduce cb)
     applied.  Returns (labels by iOrder, catalogue, nUnbound, nGroupBefore)."""
     from . import api
@@ -229,4 +229,4 @@ def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks
     sk.microstep(5, f32(0.1 * fStep))  # ... and the micro-stepped ones here
     sk.kdCalcCenter(fetch=False)
     return sk.kdUnbind(1.0, z, fCosmo, api.SPLINE, fScoop, False, flags.get("nMaxMembers", api.INT_MAX),
-                       flags["nMembers"], fetch=fetch)
+                       flags["nMembers"], fetch=fetch, out_grp=out_grp, out_cat=out_cat)
