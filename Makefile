@@ -17,6 +17,11 @@ lib: skid_b200/libskidgpu.so
 skid_b200/csrc/%.o: skid_b200/csrc/%.cu $(CUHDR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
+# unbinding: the float64 expressions of the energy scan, the centre-of-mass update and SPLINE_POT keep the
+# reference's operation order (gcc x86-64, no FMA) - no contraction into DFMA; the explicit fmaf of far_dir stay
+skid_b200/csrc/groups.o: skid_b200/csrc/groups.cu $(CUHDR)
+	$(NVCC) $(NVFLAGS) -fmad=false -c $< -o $@
+
 skid_b200/libskidgpu.so: $(CUOBJ)
 	$(NVCC) -shared -o $@ $(CUOBJ) -gencode arch=compute_100a,code=sm_100a
 
