@@ -577,6 +577,7 @@ struct UnbArgs {
 };
 
 constexpr int UNB_T = 256;
+constexpr int UNB_SM = 256;    // groups of up to this many members are unbound out of shared memory
 constexpr int UNB_MID = 1024;   // >= this many members: one block of UCL_T threads per group (k_unbind_cl<1>)
 constexpr int UNB_BIG = 16384;  // >= this many: a thread-block cluster of UCL_NB blocks per group (k_unbind_cl<UCL_NB>)
 constexpr int UCL_T = 1024;
@@ -592,6 +593,24 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 	float4 *qr = a.qr + beg, *qv = a.qv + beg;
 	int *qord = a.qord + beg;
 	double *pot = a.pot + beg;
+	// Small groups (almost all of them) are unbound out of shared memory: the swap and centre-of-mass update of a
+	// removal are a chain of dependent accesses by one thread, ~1.5 us per removal out of global memory.
+	__shared__ float4 s_qr[UNB_SM], s_qv[UNB_SM];
+	__shared__ double s_pot[UNB_SM];
+	__shared__ int s_ord[UNB_SM];
+	if (n <= UNB_SM) {
+		for (int i = tid; i < n; i += UNB_T) {
+			s_qr[i] = qr[i];
+			s_qv[i] = qv[i];
+			s_pot[i] = pot[i];
+			s_ord[i] = qord[i];
+		}
+		__syncthreads();
+		qr = s_qr;
+		qv = s_qv;
+		pot = s_pot;
+		qord = s_ord;
+	}
 	__shared__ double s_red[UNB_T / 32][7];
 	__shared__ double s_cm[7]; // dMass, rcm[3], vcm[3]
 	__shared__ float s_best[UNB_T / 32], s_least[UNB_T / 32];

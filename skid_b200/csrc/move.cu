@@ -899,7 +899,7 @@ __global__ void __launch_bounds__(256)
 
 // nScatter of the log line = surviving originals + surviving replicas (smooth1.c:517).  Grid-stride over
 // [lo, hi) with one atomic per block (one per warp serialised 570 k same-address atomics per call).
-__global__ void __launch_bounds__(256) k_count_scatter(int lo, int hi, const float4 *entNR, const uint32_t *dT,
+__global__ void __launch_bounds__(256) k_count_scatter(int lo, int hi, const float *entRho, const uint32_t *dT,
                                                        uint32_t *out)
 {
 	__shared__ uint32_t s_cnt;
@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(256) k_count_scatter(int lo, int hi, const flo
 	const float T = __uint_as_float(dT[0]);
 	uint32_t mine = 0;
 	for (int e = lo + blockIdx.x * blockDim.x + threadIdx.x; e < hi; e += gridDim.x * blockDim.x)
-		mine += entNR[e].z >= T ? 1u : 0u;
+		mine += entRho[e] >= T ? 1u : 0u; // (the compact copy of rhoEff: 4 bytes per entity instead of a 16-byte stride)
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(SK_FULL, mine, o);
 	if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
@@ -1051,7 +1051,7 @@ static void enqueue_count_scatterers(skidgpu_ctx &c, uint32_t *slot)
 	const int lo = (int)((long long)c.nEnt * c.rank / c.nranks), hi = (int)((long long)c.nEnt * (c.rank + 1) / c.nranks);
 	if (hi > lo) {
 		unsigned g = (unsigned)ceil_div(hi - lo, 256 * 8);
-		SK_LAUNCH(k_count_scatter, g > 148u * 8u ? 148u * 8u : g, 256, 0, c.stream, lo, hi, c.entNR.p, c.dT.p, slot + 1);
+		SK_LAUNCH(k_count_scatter, g > 148u * 8u ? 148u * 8u : g, 256, 0, c.stream, lo, hi, c.eRhoSorted.p, c.dT.p, slot + 1);
 	}
 }
 // close a log slot: sum over the ranks, copy to the pinned mirror, mark with an event
