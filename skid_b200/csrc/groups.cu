@@ -576,30 +576,32 @@ struct UnbArgs {
 	int nSmallMax; // groups of this many members or more are left to k_unbind_cl
 };
 
-constexpr int UNB_T = 256;
-constexpr int UNB_SM = 256;    // groups of up to this many members are unbound out of shared memory
+constexpr int UNB_TINY = 128;   // < this many members: 64 threads per group
 constexpr int UNB_MID = 1024;   // >= this many members: one block of UCL_T threads per group (k_unbind_cl<1>)
 constexpr int UNB_BIG = 16384;  // >= this many: a thread-block cluster of UCL_NB blocks per group (k_unbind_cl<UCL_NB>)
 constexpr int UCL_T = 1024;
 constexpr int UCL_NB = 8;
 
-__global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
+// T threads per group; groups of nLo <= n < nHi members; SM = capacity of the shared-memory copy.  Most groups hold
+// a few dozen members: with 256 threads for each, six of eight warps only ran the reductions (5e9 warp
+// instructions at 2^24); they now get 64.
+template <int T, int SM> __global__ void __launch_bounds__(T) k_unbind(const UnbArgs a, const int nLo, const int nHi)
 {
 	const int g = blockIdx.x + 1;
 	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const int beg = a.gStart[g];
 	int n = a.gStart[g + 1] - beg;
-	if (n >= a.nMaxMembers || n <= 0 || n >= a.nSmallMax || (g % a.nranks) != a.rank) return;
+	if (n >= a.nMaxMembers || n <= 0 || n < nLo || n >= nHi || (g % a.nranks) != a.rank) return;
 	float4 *qr = a.qr + beg, *qv = a.qv + beg;
 	int *qord = a.qord + beg;
 	double *pot = a.pot + beg;
 	// Small groups (almost all of them) are unbound out of shared memory: the swap and centre-of-mass update of a
 	// removal are a chain of dependent accesses by one thread, ~1.5 us per removal out of global memory.
-	__shared__ float4 s_qr[UNB_SM], s_qv[UNB_SM];
-	__shared__ double s_pot[UNB_SM];
-	__shared__ int s_ord[UNB_SM];
-	if (n <= UNB_SM) {
-		for (int i = tid; i < n; i += UNB_T) {
+	__shared__ float4 s_qr[SM], s_qv[SM];
+	__shared__ double s_pot[SM];
+	__shared__ int s_ord[SM];
+	if (n <= SM) {
+		for (int i = tid; i < n; i += T) {
 			s_qr[i] = qr[i];
 			s_qv[i] = qv[i];
 			s_pot[i] = pot[i];
@@ -611,15 +613,15 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 		pot = s_pot;
 		qord = s_ord;
 	}
-	__shared__ double s_red[UNB_T / 32][7];
+	__shared__ double s_red[T / 32][7];
 	__shared__ double s_cm[7]; // dMass, rcm[3], vcm[3]
-	__shared__ float s_best[UNB_T / 32], s_least[UNB_T / 32];
-	__shared__ int s_bi[UNB_T / 32], s_li[UNB_T / 32];
+	__shared__ float s_best[T / 32], s_least[T / 32];
+	__shared__ int s_bi[T / 32], s_li[T / 32];
 	__shared__ int s_iBig, s_iMin, s_stop;
 
 	// centre of mass (kd.c:1360-1375), float64 sums of float32 products
 	double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-	for (int i = tid; i < n; i += UNB_T) {
+	for (int i = tid; i < n; i += T) {
 		float4 r = qr[i], v = qv[i];
 		acc[0] += (double)v.w;
 		acc[1] += (double)__fmul_rn(v.w, r.x);
@@ -638,7 +640,7 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 	__syncthreads();
 	if (tid == 0) {
 		double t[7] = {0, 0, 0, 0, 0, 0, 0};
-		for (int ww = 0; ww < UNB_T / 32; ++ww)
+		for (int ww = 0; ww < T / 32; ++ww)
 			for (int k = 0; k < 7; ++k) t[k] += s_red[ww][k];
 		s_cm[0] = t[0];
 		for (int k = 1; k < 7; ++k) s_cm[k] = t[k] / t[0];
@@ -652,7 +654,7 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 		const double rcx = s_cm[1], rcy = s_cm[2], rcz = s_cm[3], vcx = s_cm[4], vcy = s_cm[5], vcz = s_cm[6];
 		float best = -1.0f, least = 1.0f;
 		int bi = 0x7fffffff, li = 0x7fffffff;
-		for (int i = tid; i < n; i += UNB_T) {
+		for (int i = tid; i < n; i += T) {
 			float4 r = qr[i], v = qv[i];
 			float dvx = (float)((double)a.fShift * ((double)v.x - vcx) + (double)a.fCosmo * ((double)r.x - rcx));
 			float dvy = (float)((double)a.fShift * ((double)v.y - vcy) + (double)a.fCosmo * ((double)r.y - rcy));
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 		if (tid == 0) {
 			float b = s_best[0], l = s_least[0];
 			int ib = s_bi[0], il = s_li[0];
-			for (int ww = 1; ww < UNB_T / 32; ++ww) {
+			for (int ww = 1; ww < T / 32; ++ww) {
 				if (s_best[ww] > b || (s_best[ww] == b && s_bi[ww] < ib)) {
 					b = s_best[ww];
 					ib = s_bi[ww];
@@ -754,7 +756,7 @@ __global__ void __launch_bounds__(UNB_T) k_unbind(const UnbArgs a)
 		if (a.bSubPot) { // kdSubPot (grav.c:39-60), only for pure dark / pure star inputs (kd.c:1441)
 			float4 rs = qr[n];
 			float ms = qv[n].w;
-			for (int i = tid; i < n; i += UNB_T) {
+			for (int i = tid; i < n; i += T) {
 				float4 r = qr[i];
 				float dx = __fsub_rn(rs.x, r.x), dy = __fsub_rn(rs.y, r.y), dz = __fsub_rn(rs.z, r.z);
 				float d2 = dist2_rn(dx, dy, dz);
@@ -1425,7 +1427,8 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			unsigned int hCls[4] = {0, 0, 0, 0};
 			CK(cudaMemcpyAsync(hCls, dCnt.p, sizeof hCls, cudaMemcpyDeviceToHost, s));
 			CK(cudaStreamSynchronize(s));
-			SK_LAUNCH(k_unbind, (unsigned)(G - 1), UNB_T, 0, s, ua);
+			SK_LAUNCH((k_unbind<64, UNB_TINY>), (unsigned)(G - 1), 64, 0, s, ua, 1, UNB_TINY);
+			SK_LAUNCH((k_unbind<256, 256>), (unsigned)(G - 1), 256, 0, s, ua, UNB_TINY, UNB_MID);
 			if (hCls[1] > 0) SK_LAUNCH(k_unbind_cl<1>, hCls[1], UCL_T, 0, s, ua, (const int *)clsList.p);
 			if (hCls[2] > 0) {
 				cudaLaunchConfig_t cfg = {};
