@@ -94,6 +94,7 @@ void radix_sort_pairs(uint64_t *keys, uint32_t *vals, size_t n, int bits, Worksp
 // tree.cu : 32-wide bucket tree over Morton-ordered points
 // ---------------------------------------------------------------------------------------
 #define SK_MAXLEV 10
+constexpr int TREE_KEY_BITS = 48; // sorted bits of the Morton keys (tree.cu: k_morton; move.cu: k_mover_keys)
 struct BoxTree {
 	int n = 0;          // points
 	int leaf = 32, fan = 32; // points per leaf box, children per node

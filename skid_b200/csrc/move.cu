@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) k_mover_keys(int bound, const uint32_t *d
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= bound) return;
 	if (i >= (int)*dN) { // beyond the device-side count (the host's bound is stale): sorts to the end
-		keys[i] = ~0ull;
+		keys[i] = (1ull << TREE_KEY_BITS) - 1ull;
 		vals[i] = 0u;
 		return;
 	}
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256) k_mover_keys(int bound, const uint32_t *d
 		t = fminf(fmaxf(t, 0.0f), 1.0f);
 		q[d] = min((uint32_t)(t * 2097152.0f), 2097151u);
 	}
-	keys[i] = (spread21m(q[2]) << 2) | (spread21m(q[1]) << 1) | spread21m(q[0]);
+	keys[i] = ((spread21m(q[2]) << 2) | (spread21m(q[1]) << 1) | spread21m(q[0])) >> (63 - TREE_KEY_BITS);
 	vals[i] = id;
 }
 
@@ -1094,7 +1094,7 @@ static void rebuild_tiles(skidgpu_ctx &c, StepArgs &sa, int steps)
 		uint64_t *keys = c.tKeys.alloc(bound);
 		SK_LAUNCH(k_mover_keys, (unsigned)ceil_div(bound, 256), 256, 0, s, bound, c.dT.p + DT_NACT + c.actPar, c.actList.p, c.mx.p,
 		          c.my.p, c.mz.p, c.treeM.bbox.p, keys, c.actList2.p);
-		radix_sort_pairs(keys, c.actList2.p, bound, 63, c.ws, s); // entries beyond the device-side count sort to the end
+		radix_sort_pairs(keys, c.actList2.p, bound, TREE_KEY_BITS, c.ws, s); // entries beyond the device-side count sort to the end
 		std::swap(c.actList.p, c.actList2.p);
 		std::swap(c.actList.cap, c.actList2.cap);
 	}

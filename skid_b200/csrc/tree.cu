@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(256) k_morton(const float *x, const float *y, 
 		cls = cls < 0 ? 0 : (cls > 63 ? 63 : cls);
 		key = ((uint64_t)cls << 57) | (key >> 6);
 	}
-	keys[i] = key;
+	// 48 of the 63 bits are sorted (16 per axis: cells of 1/65536 of the box, finer than the particle spacing in
+	// any realistic core; equal keys keep their input order): 6 radix passes instead of 8
+	keys[i] = key >> (63 - TREE_KEY_BITS);
 	perm[i] = (uint32_t)i;
 }
 
@@ -198,8 +200,8 @@ void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z
 	if (n == 0) return;
 	tree_bbox_only(t, x, y, z, n, s);
 	SK_LAUNCH(k_morton, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, radius, keys, perm);
-	if (dist) dist_sort_pairs(*dist, keys, perm, n, 63);
-	else radix_sort_pairs(keys, perm, n, 63, ws, s);
+	if (dist) dist_sort_pairs(*dist, keys, perm, n, TREE_KEY_BITS);
+	else radix_sort_pairs(keys, perm, n, TREE_KEY_BITS, ws, s);
 }
 
 // Leaf boxes: `leaf` consecutive sorted points per leaf (leaf = 8, 16 or 32 lanes of a warp).
