@@ -345,18 +345,7 @@ constexpr int BIG_CAP = 4096;  // ... and the ~4 % of tiles that need more take 
 		}                                                                                      \
 	}
 
-__device__ __forceinline__ uint64_t spread21m(uint32_t v)
-{
-	uint64_t x = v & 0x1fffffu;
-	x = (x | (x << 32)) & 0x1f00000000ffffull;
-	x = (x | (x << 16)) & 0x1f0000ff0000ffull;
-	x = (x | (x << 8)) & 0x100f00f00f00f00full;
-	x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
-	x = (x | (x << 2)) & 0x1249249249249249ull;
-	return x;
-}
-
-// 63-bit Morton key of the current position of every active mover (bbox = box of the initial positions)
+// 48-bit Hilbert key (common.cuh) of the current position of every active mover (bbox = box of the initial positions)
 __global__ void __launch_bounds__(256) k_mover_keys(int bound, const uint32_t *dN, const uint32_t *act, const float *mx, const float *my,
                                                     const float *mz, const float *bbox, uint64_t *keys, uint32_t *vals)
 {
@@ -375,9 +364,9 @@ __global__ void __launch_bounds__(256) k_mover_keys(int bound, const uint32_t *d
 		const float ext = bbox[3 + d] - bbox[d];
 		float t = ext > 0.0f ? (p[d] - bbox[d]) / ext : 0.0f;
 		t = fminf(fmaxf(t, 0.0f), 1.0f);
-		q[d] = min((uint32_t)(t * 2097152.0f), 2097151u);
+		q[d] = min((uint32_t)(t * 65536.0f), 65535u);
 	}
-	keys[i] = ((spread21m(q[2]) << 2) | (spread21m(q[1]) << 1) | spread21m(q[0])) >> (63 - TREE_KEY_BITS);
+	keys[i] = hilbert3(q[0], q[1], q[2], 16);
 	vals[i] = id;
 }
 

@@ -1,21 +1,10 @@
 // Stage 1: spatial index build.  Replaces kdBuildTree (kd.c:371-460; kdSelectInit 225-253,
 // UpPassInit 307-336, Combine 287-304).  The reference builds a balanced median-split binary
 // kd-tree with 16-particle buckets; tree shape does not affect any result (only tie order), so
-// the GPU index is designed for warp-wide traversal instead: points are sorted by 63-bit Morton
+// the GPU index is designed for warp-wide traversal instead: points are sorted by a 48-bit Hilbert
 // key, cut into buckets of 32 consecutive points (one coalesced 512 B float4 load per bucket),
 // and every internal node has 32 children so a warp tests all child boxes of a node at once.
 #include "ctx.cuh"
-
-__device__ __forceinline__ uint64_t spread21(uint32_t v)
-{
-	uint64_t x = v & 0x1fffffu;
-	x = (x | (x << 32)) & 0x1f00000000ffffull;
-	x = (x | (x << 16)) & 0x1f0000ff0000ffull;
-	x = (x | (x << 8)) & 0x100f00f00f00f00full;
-	x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
-	x = (x | (x << 2)) & 0x1249249249249249ull;
-	return x;
-}
 
 __global__ void k_bbox_init(float *bbox)
 {
@@ -58,14 +47,16 @@ __global__ void k_bbox_finish(float *bbox)
 	if (threadIdx.x < 6) bbox[threadIdx.x] = float_unflip(((unsigned int *)bbox)[threadIdx.x]);
 }
 
-// Sort key.  Without `radius`: 63-bit Morton code (21 bits per axis).  With `radius` (the ball radius
-// of a scatterer): [62:57] = size class (half octaves of extent/radius, largest balls first) and
-// [56:0] = 57-bit Morton code, so that a bucket of 32 consecutive scatterers holds balls of similar
-// size - the ball-inflated bucket box is then close to the balls it holds and a point inside the box
-// is likely inside the balls (tests per hit drop several-fold in clustered data).
-__global__ void __launch_bounds__(256) k_morton(const float *x, const float *y, const float *z, int n,
-                                                const float *bbox, const float *radius, uint64_t *keys,
-                                                uint32_t *perm)
+// Sort key (TREE_KEY_BITS = 48 bits).  Without `radius`: Hilbert index of the point's cell, 16 bits per axis
+// (cells of 1/65536 of the box, finer than the particle spacing in any realistic core; equal keys keep their
+// input order).  With `radius` (the ball radius of a scatterer): [47:42] = size class (half octaves of
+// extent/radius, largest balls first) and [41:0] = Hilbert index with 14 bits per axis, so that a bucket of 32
+// consecutive scatterers holds balls of similar size - the ball-inflated bucket box is then close to the balls
+// it holds and a point inside the box is likely inside the balls (tests per hit drop several-fold in clustered
+// data).
+__global__ void __launch_bounds__(256) k_sfc_keys(const float *x, const float *y, const float *z, int n,
+                                                  const float *bbox, const float *radius, uint64_t *keys,
+                                                  uint32_t *perm)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -77,22 +68,20 @@ __global__ void __launch_bounds__(256) k_morton(const float *x, const float *y, 
 		double ext = (double)bbox[3 + d] - (double)bbox[d];
 		if (ext > extMax) extMax = ext;
 		double t = ext > 0.0 ? ((double)p[d] - (double)bbox[d]) / ext : 0.0;
-		long long v = (long long)(t * 2097152.0);
+		long long v = (long long)(t * 65536.0);
 		if (v < 0) v = 0;
-		if (v > 2097151) v = 2097151;
+		if (v > 65535) v = 65535;
 		q[d] = (uint32_t)v;
 	}
-	uint64_t key = (spread21(q[2]) << 2) | (spread21(q[1]) << 1) | spread21(q[0]);
+	uint64_t key;
 	if (radius) {
 		float h = radius[i];
 		int cls = 0;
 		if (h > 0.0f && extMax > 0.0) cls = (int)floorf(2.0f * log2f((float)extMax / h));
 		cls = cls < 0 ? 0 : (cls > 63 ? 63 : cls);
-		key = ((uint64_t)cls << 57) | (key >> 6);
-	}
-	// 48 of the 63 bits are sorted (16 per axis: cells of 1/65536 of the box, finer than the particle spacing in
-	// any realistic core; equal keys keep their input order): 6 radix passes instead of 8
-	keys[i] = key >> (63 - TREE_KEY_BITS);
+		key = ((uint64_t)cls << 42) | hilbert3(q[0] >> 2, q[1] >> 2, q[2] >> 2, 14);
+	} else key = hilbert3(q[0], q[1], q[2], 16);
+	keys[i] = key;
 	perm[i] = (uint32_t)i;
 }
 
@@ -199,7 +188,7 @@ void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z
 	uint32_t *perm = t.perm.alloc(n > 0 ? n : 1);
 	if (n == 0) return;
 	tree_bbox_only(t, x, y, z, n, s);
-	SK_LAUNCH(k_morton, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, radius, keys, perm);
+	SK_LAUNCH(k_sfc_keys, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, radius, keys, perm);
 	if (dist) dist_sort_pairs(*dist, keys, perm, n, TREE_KEY_BITS);
 	else radix_sort_pairs(keys, perm, n, TREE_KEY_BITS, ws, s);
 }
