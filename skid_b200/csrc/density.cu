@@ -278,6 +278,8 @@ __device__ __forceinline__ void knn_walk(const KnnArgs &a, const KnnQuery &q, ui
 // their distances to the new query is an upper bound of its k-th distance before anything else is known: the
 // phase-A buckets and the walk then only stage what can still enter, and a query needs ~k/32 + 1 merges instead
 // of ~10 (the merges were 39 % of the kernel's instructions, profiles/r01_v6_knn_2e22_lines.txt).
+// (61 registers, 4 blocks per SM.  Measured: 51 registers / 5 blocks 68.0 ms, 42 registers / 6 blocks with spills
+// 69.9 ms, against 67.7 ms - occupancy is not what limits it; 4, 16 or 32 queries per warp: 67.9 / 68.6 / 70.0 ms.)
 template <int R> __global__ void __launch_bounds__(KNN_WARPS * 32) k_knn_density(const KnnArgs a)
 {
 	__shared__ uint64_t s_buf[KNN_WARPS][64];

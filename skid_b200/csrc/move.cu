@@ -741,6 +741,17 @@ struct TileShared {
 // now travel with asynchronous copies (cp.async, 16 bytes each, LDGSTS in SASS) into one of two buffers while the
 // previous chunk is being evaluated; the list indices of the chunk after that are already in registers.
 // (Measured per pass at 2^24: synchronous 168 ms, 2 x 128 records 155 ms, 4 x 64 records 165 ms, 3 x 128 188 ms.)
+// Also measured and dropped: two phases per chunk - the 16 hit tests of a lane branch-free into a bit mask, then
+// the spline terms of the set bits only (recomputing dx, dy, dz): 149 -> 185 ms.  The hits are not spread evenly
+// (a list is ordered along the scatterers' curve: some chunks hit with nearly every record, others with none, and
+// the test loop already skips the term warp-wide there), so the mask loop runs max-over-lanes popc times on top
+// of the recomputation.
+// ncu on this version (profiles/r02b_tilestep_2e24_*): issue active 82 %, the shared-memory pipe at 70 % (LDS.128 of
+// records 32 bytes apart: 2-way bank conflicts), 51 % of the warp instructions in the spline term at 12.8 of 32
+// lanes.  Measured against it, each within +-3 %: a split [pos | norm] buffer without the conflicts (+2 ms), the
+// term without the two Newton refinements and with FMA accumulation (8 of its 27 instructions; -5 ms, not worth
+// three more ulp per term), the test loop unrolled by 2 or 4 (+2, +4 ms).  With both units near their limit and
+// ~10 warps per scheduler, relieving one of them leaves the other.
 __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, TileShared &sh)
 {
 	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
