@@ -272,7 +272,6 @@ def main():
     reducer = None
     if shard:
         parallel.init_comm(sk, dist, rank, world)           # the library's own NCCL communicator
-        reducer = parallel.Reducer(dist, dev0, sk.stream())  # only used by upload_sliced (host -> device slices)
     tau = float(np.float32(fl["tau"]))
     fCvg = float(np.float32(0.5 * tau))
     fScoop = float(np.float32(2.0 * tau))
@@ -416,7 +415,7 @@ def main():
                    "unbound": st["unbound"]},
         "stage_ms": st["stage_ms"],
         "knn_queries_per_s": (n / nshare) * nshare / (knn_ms * 1e-3) if knn_ms > 0 else None,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_aos.nbytes),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_aos.nbytes),  # whole job: every rank uploads 1/N of the snapshot
                 "d2h_bytes_per_step": int(st_e["d2h"]), "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": int(st["launches"]),
         "clocks": clocks,

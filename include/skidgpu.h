@@ -95,7 +95,9 @@ long long skidgpu_comm_bytes(skidgpu_ctx *ctx, long long *nCalls);
 int skidgpu_set_shard(skidgpu_ctx *ctx, int rank, int nranks);
 
 /* What kdReadTipsy (kd.c:122-222, main.c:348) leaves in kd->pInit: n = nGas+nDark+nStar
- * particles in file order (gas, dark, star), p[i].iOrder == i.  fTime = header time. */
+ * particles in file order (gas, dark, star), p[i].iOrder == i.  fTime = header time.
+ * With a communicator (skidgpu_comm_init, nranks > 1) the call is collective: every rank passes the same
+ * snapshot, uploads only its 1/nranks slice of it and the slices are all-gathered between the GPUs. */
 int skidgpu_set_particles(skidgpu_ctx *ctx, const skidgpu_pinit *p, int n, int nGas,
                           int nDark, int nStar);
 

@@ -219,8 +219,20 @@ extern "C" int skidgpu_set_particles(skidgpu_ctx *ctx, const skidgpu_pinit *p, i
 	set_counts(ctx, n, nGas, nDark, nStar);
 	for (int i = 0; i < n; i += (n > 4096 ? n / 7 + 1 : 1))
 		if (p[i].iOrder != i) throw SkidError("skidgpu_set_particles: particles must be in file order (iOrder == index)");
-	skidgpu_pinit *d = ctx->aos.alloc(n);
-	CK(cudaMemcpyAsync(d, p, sizeof(skidgpu_pinit) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	skidgpu_pinit *d;
+	if (ctx->comm && ctx->nranks > 1) {
+		// sharded run: every rank holds the same host snapshot (the premise of every collective stage call), so
+		// the records need not cross PCIe N times - each rank uploads its 1/N slice and the slices are all-gathered
+		// over NVLink (6.4 GB -> 0.8 GB of host->device traffic per rank at 2^27 on 8 GPUs)
+		const size_t chunk = ceil_div((size_t)n, (size_t)ctx->nranks);
+		d = ctx->aos.alloc(chunk * ctx->nranks);
+		const size_t lo = std::min((size_t)n, chunk * ctx->rank), hi = std::min((size_t)n, chunk * (ctx->rank + 1));
+		if (hi > lo) CK(cudaMemcpyAsync(d + lo, p + lo, sizeof(skidgpu_pinit) * (hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+		sk_allgather(*ctx, d, (long long)(chunk * sizeof(skidgpu_pinit)), SK_U8);
+	} else {
+		d = ctx->aos.alloc(n);
+		CK(cudaMemcpyAsync(d, p, sizeof(skidgpu_pinit) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+	}
 	SK_LAUNCH(k_aos_to_soa, (unsigned)ceil_div(n, 256), 256, 0, ctx->stream, n, d, ctx->x.p, ctx->y.p, ctx->z.p, ctx->vx.p,
 	          ctx->vy.p, ctx->vz.p, ctx->mass.p, ctx->soft.p, ctx->temp.p);
 	CK(cudaStreamSynchronize(ctx->stream));

@@ -162,41 +162,6 @@ def merge_labels(dist, labels):
     return labels
 
 
-def upload_sliced(reducer, pinit, rank, nranks):
-    """Host AoS (PINIT records, 12 x 4 bytes) -> 9 replicated device SoA columns (x y z vx vy vz mass soft temp):
-    slice upload + device transpose + all-gather.  Returns [slice buffer, 9 column tensors]; the caller keeps
-    them alive until the library has copied the columns (skidgpu_set_particles_dev synchronises)."""
-    dist, dev = reducer.dist, reducer.device
-    n = len(pinit)
-    per = -(-n // nranks)                       # equal chunks (all_gather_into_tensor), last one padded
-    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
-    raw = torch.from_numpy(np.ascontiguousarray(pinit).view(np.float32).reshape(n, 12))
-    # host -> device on torch's own stream: pinned host blocks remember the streams that read them, and the
-    # context's stream (owned by the library) may be gone by the time torch releases the host buffer
-    mine = torch.zeros((per, 12), dtype=torch.float32, device=dev)
-    if hi > lo:
-        mine[:hi - lo].copy_(raw[lo:hi], non_blocking=True)
-    torch.cuda.current_stream(dev).synchronize()
-    ctx = torch.cuda.stream(reducer.stream) if reducer.stream is not None else _nullcontext()
-    cols = [mine]  # kept alive by the caller until the context's stream has been synchronised
-    with ctx:
-        full = torch.empty((nranks * per,), dtype=torch.float32, device=dev)
-        for k in range(9):
-            dist.all_gather_into_tensor(full, mine[:, k].contiguous())
-            cols.append(full[:n].clone())
-    reducer.bytes += 9 * 4 * n
-    reducer.h2d_bytes = getattr(reducer, "h2d_bytes", 0) + 48 * (hi - lo)
-    return cols
-
-
-class _nullcontext:
-    def __enter__(self):
-        return None
-
-    def __exit__(self, *a):
-        return False
-
-
 def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks, host=True, dev_ptrs=None,
                      fetch=True, out_grp=None, out_cat=None):
     """The main.c stage script on a sharded snapshot.  sk: api.SkidGPU with comm_init (or set_shard + reduce cb)
@@ -211,14 +176,9 @@ def run_skid_sharded(sk, reducer, pinit, nGas, nDark, nStar, flags, rank, nranks
     a32 = f32(1.0 / (1.0 + z))
     fCosmo = a32 * api.csmExp2Hub(a32, f32(flags["H0"]), f32(flags.get("Omega0", 1.0)), f32(flags.get("Lambda", 0.0)))
     sk.log = []
-    if host and nranks > 1 and reducer is not None and reducer.device.type == "cuda":
-        # the snapshot is replicated on the devices but need not cross PCIe N times: every rank uploads its
-        # 1/N slice of the host AoS, transposes it to SoA columns on the device and the columns are
-        # all-gathered over NVLink (N x fewer host->device bytes per rank)
-        cols = upload_sliced(reducer, pinit, rank, nranks)
-        sk.set_particles_dev([t.data_ptr() for t in cols[1:]], len(pinit), nGas, nDark, nStar)  # copies and synchronises
-        del cols  # released while the context's stream is still alive (NCCL recorded it on these blocks)
-    elif host:
+    if host:
+        # with a communicator the library uploads this rank's 1/N slice of the host AoS and all-gathers the
+        # slices over NVLink (csrc/api.cu: skidgpu_set_particles)
         sk.set_particles(pinit, nGas, nDark, nStar)
     else:
         sk.set_particles_dev(dev_ptrs, len(pinit), nGas, nDark, nStar)
