@@ -141,11 +141,40 @@ __global__ void __launch_bounds__(256) k_uf_init(int n, uint32_t *parent)
 	if (i < n) parent[i] = (uint32_t)i;
 }
 
+// Bounding box of every cell's movers (one warp per cell): lets k_link_cells decide most cell pairs without
+// looking at a single mover pair.
+__global__ void __launch_bounds__(256) k_cell_boxes(int nCells, const uint32_t *cellStart, const float4 *spos, float4 *cellBox)
+{
+	const int lane = threadIdx.x & 31;
+	const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (c >= nCells) return;
+	const uint32_t beg = cellStart[c], end = cellStart[c + 1];
+	float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+	for (uint32_t i = beg + lane; i < end; i += 32) {
+		const float4 p = spos[i];
+		lo[0] = fminf(lo[0], p.x), hi[0] = fmaxf(hi[0], p.x);
+		lo[1] = fminf(lo[1], p.y), hi[1] = fmaxf(hi[1], p.y);
+		lo[2] = fminf(lo[2], p.z), hi[2] = fmaxf(hi[2], p.z);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			lo[d] = fminf(lo[d], __shfl_xor_sync(SK_FULL, lo[d], o));
+			hi[d] = fmaxf(hi[d], __shfl_xor_sync(SK_FULL, hi[d], o));
+		}
+	if (lane == 0) {
+		cellBox[2 * (size_t)c] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+		cellBox[2 * (size_t)c + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+	}
+}
+
 struct LinkArgs {
 	int nCells;
 	const uint32_t *cellStart;
 	const uint64_t *cellKey;
 	const float4 *spos;
+	const float4 *cellBox; // [2c] = lo, [2c+1] = hi of the movers of cell c
 	const uint64_t *hkeys;
 	const uint32_t *hvals;
 	uint32_t hmask;
@@ -169,7 +198,8 @@ __global__ void __launch_bounds__(256) k_link_cells(const LinkArgs a)
 	const int R = a.g.R, W = 2 * R + 1;
 	const int nOff = W * W * W;
 	const uint32_t aBeg = a.cellStart[A], aEnd = a.cellStart[A + 1];
-	const int nA = (int)(aEnd - aBeg);
+	const uint32_t nA = aEnd - aBeg;
+	const float4 alo = a.cellBox[2 * (size_t)A], ahi = a.cellBox[2 * (size_t)A + 1];
 	for (int base = nOff / 2 + 1; base < nOff; base += 32) {
 		int o = base + lane;
 		int B = -1;
@@ -194,6 +224,30 @@ __global__ void __launch_bounds__(256) k_link_cells(const LinkArgs a)
 			int src = __ffs(have) - 1;
 			have &= have - 1;
 			int Bc = __shfl_sync(SK_FULL, B, src);
+			// The boxes of the two cells' movers decide most pairs of cells: converged clumps are much smaller than
+			// a cell, so two clumps farther apart than tau are rejected and two clumps well within tau are united
+			// without a mover-pair test.  (ncu on the version that always scanned the pairs: 11.3 ms at 2^24 for
+			// 4.7e8 warp instructions, 23 % warps active - a few warps scanning the nA x nB ~ 10^5 pairs of two
+			// unlinked dense cells, through a 64-bit division per pair, were the whole kernel.)  The bounds are a
+			// lower / upper bound of the min-image distance of any pair, with a 1e-5 margin on tau^2 for the
+			// float rounding of the exact test (coordinate differences this small are exact in float32).
+			const float4 blo = a.cellBox[2 * (size_t)Bc], bhi = a.cellBox[2 * (size_t)Bc + 1];
+			float gl2 = 0.0f, gh2 = 0.0f;
+			{
+				const float al[3] = {alo.x, alo.y, alo.z}, ah[3] = {ahi.x, ahi.y, ahi.z};
+				const float bl[3] = {blo.x, blo.y, blo.z}, bh[3] = {bhi.x, bhi.y, bhi.z};
+#pragma unroll
+				for (int d = 0; d < 3; ++d) {
+					const float direct = fmaxf(fmaxf(bl[d] - ah[d], al[d] - bh[d]), 0.0f);
+					const float span = fmaxf(ah[d], bh[d]) - fminf(al[d], bl[d]);
+					const float wrapped = fmaxf(a.L[d] - span, 0.0f); // the other way round the periodic axis
+					const float gmin = fminf(direct, wrapped);
+					const float sep = fmaxf(ah[d] - bl[d], bh[d] - al[d]);
+					gl2 = fmaf(gmin, gmin, gl2);
+					gh2 = fmaf(sep, sep, gh2);
+				}
+			}
+			if (gl2 > a.fTau2 * 1.00001f) continue; // no mover of A is within tau of a mover of B
 			// already in the same component?
 			uint32_t ra = 0, rb = 1;
 			if (lane == 0) {
@@ -203,23 +257,28 @@ __global__ void __launch_bounds__(256) k_link_cells(const LinkArgs a)
 			ra = __shfl_sync(SK_FULL, ra, 0);
 			rb = __shfl_sync(SK_FULL, rb, 0);
 			if (ra == rb) continue;
-			const uint32_t bBeg = a.cellStart[Bc], bEnd = a.cellStart[Bc + 1];
-			const int nB = (int)(bEnd - bBeg);
-			const long long nPairs = (long long)nA * nB;
-			bool linked = false;
-			for (long long pbase = 0; pbase < nPairs && !linked; pbase += 32) {
-				long long pi = pbase + lane;
-				bool hit = false;
-				if (pi < nPairs) {
-					float4 pa = a.spos[aBeg + (uint32_t)(pi / nB)];
-					float4 pb = a.spos[bBeg + (uint32_t)(pi % nB)];
-					// kd.c:871-875 with the query shifted by +-L first (INTERCONT)
-					float dx = minimg_dx(pa.x, __fadd_rn(pa.x, a.L[0]), __fsub_rn(pa.x, a.L[0]), a.hL[0], pb.x);
-					float dy = minimg_dx(pa.y, __fadd_rn(pa.y, a.L[1]), __fsub_rn(pa.y, a.L[1]), a.hL[1], pb.y);
-					float dz = minimg_dx(pa.z, __fadd_rn(pa.z, a.L[2]), __fsub_rn(pa.z, a.L[2]), a.hL[2], pb.z);
-					hit = dist2_rn(dx, dy, dz) < a.fTau2;
+			bool linked = gh2 < a.fTau2 * 0.99999f;     // every mover of A is within tau of every mover of B
+			if (!linked) {
+				const uint32_t bBeg = a.cellStart[Bc], bEnd = a.cellStart[Bc + 1];
+				const uint32_t nB = bEnd - bBeg;
+				const unsigned long long nPairs = (unsigned long long)nA * nB;
+				for (unsigned long long pbase = 0; pbase < nPairs && !linked; pbase += 32) {
+					const unsigned long long pi = pbase + lane;
+					bool hit = false;
+					if (pi < nPairs) {
+						uint32_t ia, ib;
+						if (nPairs <= 0xffffffffull) ia = (uint32_t)pi / nB, ib = (uint32_t)pi - ia * nB; // 32-bit division
+						else ia = (uint32_t)(pi / nB), ib = (uint32_t)(pi % nB);
+						float4 pa = a.spos[aBeg + ia];
+						float4 pb = a.spos[bBeg + ib];
+						// kd.c:871-875 with the query shifted by +-L first (INTERCONT)
+						float dx = minimg_dx(pa.x, __fadd_rn(pa.x, a.L[0]), __fsub_rn(pa.x, a.L[0]), a.hL[0], pb.x);
+						float dy = minimg_dx(pa.y, __fadd_rn(pa.y, a.L[1]), __fsub_rn(pa.y, a.L[1]), a.hL[1], pb.y);
+						float dz = minimg_dx(pa.z, __fadd_rn(pa.z, a.L[2]), __fsub_rn(pa.z, a.L[2]), a.hL[2], pb.z);
+						hit = dist2_rn(dx, dy, dz) < a.fTau2;
+					}
+					linked = __any_sync(SK_FULL, hit);
 				}
-				linked = __any_sync(SK_FULL, hit);
 			}
 			if (linked && lane == 0) uf_union(a.parent, (uint32_t)A, (uint32_t)Bc);
 			__syncwarp();
@@ -339,7 +398,7 @@ void stage_fof(skidgpu_ctx &c, float fTau, int *nGroupOut)
 
 	DevBuf<uint32_t> cellStart, moverCell, hvals, parent, minOrd;
 	DevBuf<uint64_t> cellKey, hkeys;
-	DevBuf<float4> spos;
+	DevBuf<float4> spos, cellBox;
 	cellStart.alloc(nCells + 1);
 	cellKey.alloc(nCells);
 	moverCell.alloc(m);
@@ -348,6 +407,8 @@ void stage_fof(skidgpu_ctx &c, float fTau, int *nGroupOut)
 	          moverCell.p, nCells);
 	SK_LAUNCH(k_gather_sorted_movers, (unsigned)ceil_div(m, 256), 256, 0, s, m, idx, c.mx.p, c.my.p, c.mz.p, c.mOrd.p,
 	          spos.p);
+	cellBox.alloc(2 * (size_t)nCells);
+	SK_LAUNCH(k_cell_boxes, (unsigned)ceil_div((size_t)nCells * 32, 256), 256, 0, s, nCells, cellStart.p, spos.p, cellBox.p);
 	uint32_t hcap = 64;
 	while (hcap < 2u * (uint32_t)nCells) hcap <<= 1;
 	hkeys.alloc(hcap);
@@ -362,6 +423,7 @@ void stage_fof(skidgpu_ctx &c, float fTau, int *nGroupOut)
 	la.cellStart = cellStart.p;
 	la.cellKey = cellKey.p;
 	la.spos = spos.p;
+	la.cellBox = cellBox.p;
 	la.hkeys = hkeys.p;
 	la.hvals = hvals.p;
 	la.hmask = hcap - 1;
