@@ -56,6 +56,28 @@ struct KernelSpans {
 	}
 };
 
+// Scratch of the FoF and unbinding stages.  These used to be locals of the stage functions (allocated from the
+// stream-ordered pool and freed on every call); on the massive-halo box the pool then sometimes needed
+// 0.1 - 0.7 s to carve the FoF buffers out of what the unbinding stage of the previous pass had left behind
+// (measured with events around the section; the kernels themselves are stable).  They live as long as the
+// context and only grow.
+struct FofScratch {
+	DevBuf<uint32_t> cellStart, moverCell, hvals, parent, minOrd;
+	DevBuf<uint64_t> cellKey, hkeys;
+	DevBuf<float4> spos, cellBox;
+};
+struct UnbindScratch {
+	DevBuf<uint32_t> order, tiles, tileStart, scCnt, scStart, scList, cntU, idx0;
+	DevBuf<uint64_t> keys;
+	DevBuf<int> gStart, qord, map, clsList, cpack;
+	DevBuf<float4> qr, qv, posS;
+	DevBuf<float> softS, sx, sy, sz, pack;
+	DevBuf<double> pot;
+	DevBuf<unsigned int> dCnt;
+	DevBuf<skidgpu_pgroup> cat2;
+	BoxTree treeS;
+};
+
 struct skidgpu_ctx {
 	int device = 0;
 	cudaStream_t stream = 0;
@@ -151,6 +173,9 @@ struct skidgpu_ctx {
 	DevBuf<skidgpu_pgroup> gCat;
 	std::vector<skidgpu_pgroup> hCat;
 	bool haveCenters = false;
+
+	FofScratch fofS;
+	UnbindScratch unbS;
 
 	// ---- timing / counters
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -396,9 +396,10 @@ void stage_fof(skidgpu_ctx &c, float fTau, int *nGroupOut)
 	CK(cudaStreamSynchronize(s));
 	const int nCells = (int)nCellsU;
 
-	DevBuf<uint32_t> cellStart, moverCell, hvals, parent, minOrd;
-	DevBuf<uint64_t> cellKey, hkeys;
-	DevBuf<float4> spos, cellBox;
+	FofScratch &S = c.fofS; // persistent scratch (ctx.cuh)
+	auto &cellStart = S.cellStart, &moverCell = S.moverCell, &hvals = S.hvals, &parent = S.parent, &minOrd = S.minOrd;
+	auto &cellKey = S.cellKey, &hkeys = S.hkeys;
+	auto &spos = S.spos, &cellBox = S.cellBox;
 	cellStart.alloc(nCells + 1);
 	cellKey.alloc(nCells);
 	moverCell.alloc(m);
@@ -451,5 +452,5 @@ void stage_fof(skidgpu_ctx &c, float fTau, int *nGroupOut)
 	SK_LAUNCH(k_assign_gid, (unsigned)ceil_div(m, 256), 256, 0, s, m, moverCell.p, spos.p, parent.p, minOrd.p, scan,
 	          gid, repOrd);
 	if (nGroupOut) *nGroupOut = c.nGroup;
-	tm.stop(); // synchronises before the local DevBufs are freed
+	tm.stop();
 }

@@ -1236,16 +1236,17 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 	StageTimer tm(c, 5);
 	const int G = c.nGroup;
 	if (nGroupBeforeOut) *nGroupBeforeOut = G - 1;
-	DevBuf<uint32_t> order, tiles, tileStart, scCnt, scStart, scList, cntU;
-	DevBuf<uint64_t> keys;
-	DevBuf<int> gStart, qord, map;
-	DevBuf<float4> qr, qv, posS;
-	DevBuf<float> softS, sx, sy, sz;
-	DevBuf<double> pot;
-	DevBuf<unsigned int> dCnt;
-	DevBuf<unsigned long long> dPairs;
-	DevBuf<skidgpu_pgroup> cat2;
-	BoxTree treeS;
+	UnbindScratch &S = c.unbS; // persistent scratch (ctx.cuh)
+	auto &order = S.order, &tiles = S.tiles, &tileStart = S.tileStart, &scCnt = S.scCnt, &scStart = S.scStart, &scList = S.scList,
+	     &cntU = S.cntU;
+	auto &keys = S.keys;
+	auto &gStart = S.gStart, &qord = S.qord, &map = S.map;
+	auto &qr = S.qr, &qv = S.qv, &posS = S.posS;
+	auto &softS = S.softS, &sx = S.sx, &sy = S.sy, &sz = S.sz;
+	auto &pot = S.pot;
+	auto &dCnt = S.dCnt;
+	auto &cat2 = S.cat2;
+	BoxTree &treeS = S.treeS;
 	unsigned int hUnbound = 0;
 
 	if (G > 1) {
@@ -1282,7 +1283,7 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			softS.alloc(n0 > 0 ? n0 : 1);
 		}
 		if (!reuseA && n0 > 0) {
-			DevBuf<uint32_t> idx0;
+			auto &idx0 = S.idx0;
 			idx0.alloc(n0);
 			sx.alloc(n0);
 			sy.alloc(n0);
@@ -1296,7 +1297,6 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			SK_LAUNCH(k_gather_scoop_sorted, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, treeS.perm.p, idx0.p, c.x.p,
 			          c.y.p, c.z.p, c.mass.p, c.soft.p, posS.p, softS.p);
 			tree_build_boxes(treeS, posS.p, nullptr, nullptr, n0, s);
-			CK(cudaStreamSynchronize(s)); // idx0 goes out of scope
 		}
 		ScoopArgs sc;
 		sc.tv = tree_view(reuseA ? c.treeA : treeS);
@@ -1420,7 +1420,7 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			ua.nranks = c.nranks;
 			ua.nSmallMax = UNB_MID;
 			// size classes: small groups one 256-thread block each, large ones 1024 threads, the largest a cluster
-			DevBuf<int> clsList;
+			auto &clsList = S.clsList;
 			clsList.alloc(2 * (size_t)G + 2);
 			SK_LAUNCH(k_unbind_classes, (unsigned)ceil_div(G, 256), 256, 0, s, G, c.gN.p, nMaxMembers, c.rank, c.nranks,
 			          clsList.p, dCnt.p);
@@ -1446,8 +1446,8 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 				++g_skid_launches;
 			}
 			if (c.nranks > 1) { // merge the shards: labels (owner wrote 0 for unbound members), rows, count
-				DevBuf<float> pack;
-				DevBuf<int> cpack;
+				auto &pack = S.pack;
+				auto &cpack = S.cpack;
 				pack.alloc((size_t)G * 8);
 				cpack.alloc((size_t)G + 1);
 				sk_reduce(c, c.gid.p, n, SK_I32, SK_MIN);
@@ -1497,6 +1497,6 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 		SK_LAUNCH(k_group_radius, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, c.x.p, c.y.p, c.z.p, c.L[0], c.L[1],
 		          c.L[2], c.gCat.p);
 	}
-	tm.stop(); // synchronises before the local DevBufs are freed
+	tm.stop();
 }
 

@@ -385,6 +385,9 @@ __global__ void __launch_bounds__(256) k_mover_keys(int bound, const uint32_t *d
 		cand = (p).w > 0.0f && (u_ <= 0.0f || u_ * u_ <= 4.0004f * (p).w * r2);                \
 	}
 
+// (Measured and dropped: a cheap pre-test of the bucket's scatterers against the members' bounding box before
+// the 8-member test - in the dense cores this kernel serves nearly every visited bucket holds a candidate, the
+// pre-test only adds to it: list builds 80 -> 84 ms per pass.)
 // Slow path of the tile build: the tiles in `queue` walk the tree themselves; nodes and leaf buckets are
 // pruned against the members (not only their bounding box), so a tile that straddles a Morton
 // discontinuity still gets a short list.

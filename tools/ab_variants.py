@@ -44,8 +44,7 @@ def child(log2n, kind, lib):
     tot = sum(st.values()) if isinstance(st, dict) else float(sum(st))
     print(json.dumps(dict(lib=lib, total_ms=tot, stage_ms=st, kernel_ms=last["kernel_ms"], groups=last["groups"],
                           unbound=last["unbound"], ittr=last["ittr"], launches=last["launches"],
-                          prev_total=[sum(r["stage_ms"].values()) if isinstance(r["stage_ms"], dict) else float(sum(r["stage_ms"]))
-                                      for r in rows[:-1]])), flush=True)
+                          prev_stage_ms=[{k: round(v, 1) for k, v in r["stage_ms"].items()} for r in rows[:-1]])), flush=True)
     sk.close()
 
 
