@@ -98,6 +98,14 @@ def tensor_from_pointer(ptr, count, dtype, device):
     return torch.from_numpy(np.frombuffer(buf, dtype=_NP[dtype]))
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
 class Reducer:
     """skidgpu_reduce_cb implementation over torch.distributed.  `stream` = the context's CUDA stream
     (int handle) so that collectives are ordered with the library's kernels; None on CPU."""
@@ -133,10 +141,15 @@ class Reducer:
                 if count <= 16:  # only the small per-step buffers are worth caching (large ones get reallocated)
                     self._alias[key] = t
             if dtype == 1 and op != 2:
-                # NCCL has no uint8 min/max guarantee across versions: widen flags through int32
-                w = t.to(torch.int32)
-                self.reduce_tensor(w, op)
-                t.copy_(w.to(torch.uint8))
+                # NCCL has no uint8 min/max guarantee across versions: widen flags through int32.  The conversions
+                # must run on the context's stream like the collective itself: on torch's default stream they raced
+                # with the library's kernels before and after the exchange (the touched flags of the initial cut -
+                # an intermittent 131 instead of 120 FoF groups on the demo through this shim)
+                ctx = torch.cuda.stream(self.stream) if self.stream is not None else _NullCtx()
+                with ctx:
+                    w = t.to(torch.int32)
+                    self.reduce_tensor(w, op)
+                    t.copy_(w.to(torch.uint8))
             else:
                 self.reduce_tensor(t, op)
             self.host_s += time.perf_counter() - t0
