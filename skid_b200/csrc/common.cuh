@@ -147,14 +147,13 @@ struct BoxTree {
 	DevBuf<float> bbox;    // 6 floats lo[3], hi[3]
 };
 
-// Sort n points (x,y,z arrays) by 63-bit Morton key; fills t.perm.  If lohi != nullptr it gives the
-// normalisation box (host floats lo[3],hi[3]) else the bounding box is reduced on the device.
-// radius (nullable): per-point ball radius; when given the sort key is (size class, Morton) - tree.cu.
+// Sort n points (x,y,z arrays) by their 48-bit Hilbert key (tree.cu); fills t.perm.  The bounding box is reduced
+// on the device.
 // dist (nullable): a context with nranks > 1 whose ranks all hold the same points - the sort is then shared
 // between the ranks (every rank sorts one key range, the pieces are all-gathered); same result.
 struct skidgpu_ctx;
 void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z, int n,
-                      Workspace &ws, cudaStream_t s, const float *radius = nullptr, skidgpu_ctx *dist = nullptr);
+                      Workspace &ws, cudaStream_t s, skidgpu_ctx *dist = nullptr);
 void tree_bbox_only(BoxTree &t, const float *x, const float *y, const float *z, int n, cudaStream_t s);
 // Build the box levels over sorted points pos4[0..n) (xyz used).  infl (nullable): per-point
 // inflation radius (sorted order); aux (nullable): per-point value whose max goes to lo.w.

@@ -1293,7 +1293,7 @@ void stage_unbind(skidgpu_ctx &c, float fG, float z, double fCosmoD, int iSoftTy
 			SK_LAUNCH(k_label_compact, (unsigned)ceil_div(n, 256), 256, 0, s, n, c.gid.p, flags, scan, (uint64_t *)nullptr, idx0.p);
 			SK_LAUNCH(k_gather_scoop_src, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, idx0.p, c.x.p, c.y.p, c.z.p, sx.p,
 			          sy.p, sz.p);
-			tree_sort_points(treeS, sx.p, sy.p, sz.p, n0, c.ws, s, nullptr, &c);
+			tree_sort_points(treeS, sx.p, sy.p, sz.p, n0, c.ws, s, &c);
 			SK_LAUNCH(k_gather_scoop_sorted, (unsigned)ceil_div(n0, 256), 256, 0, s, n0, treeS.perm.p, idx0.p, c.x.p,
 			          c.y.p, c.z.p, c.mass.p, c.soft.p, posS.p, softS.p);
 			tree_build_boxes(treeS, posS.p, nullptr, nullptr, n0, s);

@@ -472,20 +472,42 @@ __global__ void __launch_bounds__(128, MINB) k_tile_walk(const StepArgs a, const
 				}
 				const int c = __ffs(mk) - 1;
 				mk &= mk - 1;
-				if (lane == lev) mymask = mk;
 				if (lev > 0) {
+					if (lane == lev) mymask = mk;
 					--lev;
 					node = node * 32 + c;
 					TILE_TEST_CHILDREN();
 					continue;
 				}
-				const uint32_t e = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
-				const float4 p = a.entPos[e];
-				const float rho = a.entRho[e];
-				bool cand;
-				TILE_MEMBER_TEST(p, cand);
-				cand = cand && rho >= T; // dead scatterers never come back
-				TILE_APPEND(cand, e);
+				// all the buckets of this node, in order, the records of the next one in flight while this one is
+				// tested (a walk is a chain of dependent loads: one warp alone runs at a few per cent of an issue slot;
+				// the launch list shows ~400 us per rebuild whether 4 or 200 million instructions are executed - the
+				// latency of one tile's walk.  Measured at 2^24: list builds 79.6 -> 73.7 ms, on the massive-halo box
+				// builds 53.9 -> 49.2 and the per-step short-tile walks 34.3 -> 29.1 ms; 6 or 5 blocks per SM with
+				// 80 / 96 registers instead of 8 with 64: 74.6 / 75.8 ms)
+				if (lane == 0) mymask = 0u;
+				uint32_t e = (node * 32 + c) * 32 + lane; // arrays are padded with fBall2 = -1 dummies
+				float4 p = a.entPos[e];
+				float rho = a.entRho[e];
+				while (true) {
+					const bool more = mk != 0u;
+					uint32_t en = 0u;
+					float4 pn = p;
+					float rhon = 0.0f;
+					if (more) {
+						const int c1 = __ffs(mk) - 1;
+						mk &= mk - 1;
+						en = (node * 32 + c1) * 32 + lane;
+						pn = a.entPos[en];
+						rhon = a.entRho[en];
+					}
+					bool cand;
+					TILE_MEMBER_TEST(p, cand);
+					cand = cand && rho >= T; // dead scatterers never come back
+					TILE_APPEND(cand, e);
+					if (overflow || !more) break;
+					e = en, p = pn, rho = rhon;
+				}
 			}
 #undef TILE_TEST_CHILDREN
 			if (!overflow && attempt == 1 && shortQueue && lane == 0) shortQueue[atomicAdd(shortCount, 1u)] = (uint32_t)t;
@@ -644,7 +666,8 @@ __global__ void __launch_bounds__(128) k_tile_filter(const StepArgs a)
 	{
 		// (A two-pass variant - bounding-box pretest of the tile, survivors compacted in shared memory, member test
 		// on the dense survivors - was measured and dropped: the box of 8 members rejects too little of the
-		// supertile's superset to pay for the compaction; list builds 117 -> 135 ms per pass.)
+		// supertile's superset to pay for the compaction; list builds 117 -> 135 ms per pass.  Nor does fetching the
+		// next 32 records while the current ones are tested: 56 -> 64 registers, builds 73.5 -> 79.8 ms.)
 		bool overflow = false;
 		for (int s0 = 0; s0 < ns && !overflow; s0 += 32) {
 			const uint32_t e = eN;
@@ -754,7 +777,8 @@ struct TileShared {
 // lanes.  Measured against it, each within +-3 %: a split [pos | norm] buffer without the conflicts (+2 ms), the
 // term without the two Newton refinements and with FMA accumulation (8 of its 27 instructions; -5 ms, not worth
 // three more ulp per term), the test loop unrolled by 2 or 4 (+2, +4 ms).  With both units near their limit and
-// ~10 warps per scheduler, relieving one of them leaves the other.
+// ~10 warps per scheduler, relieving one of them leaves the other.  Fetching the first chunk's list entries from the
+// tile's small slot before count and offset are known (one dependent round trip less per block): +2 ms.
 __device__ __forceinline__ void tile_step_body(const StepArgs &a, const int t, TileShared &sh)
 {
 	const int j = threadIdx.x & (LPM - 1), m = threadIdx.x / LPM;
@@ -1217,7 +1241,7 @@ void stage_move(skidgpu_ctx &c, float fDensMin, float fTempMax, float fMassMax, 
 		SK_LAUNCH(k_compact_idx2, (unsigned)ceil_div(n, 256), 256, 0, s, n, flags, scan, fileIdx);
 		float *gx = c.tmpx.alloc(m), *gy = c.tmpy.alloc(m), *gz = c.tmpz.alloc(m);
 		SK_LAUNCH(k_gather3b, (unsigned)ceil_div(m, 256), 256, 0, s, m, fileIdx, c.x.p, c.y.p, c.z.p, gx, gy, gz);
-		tree_sort_points(c.treeM, gx, gy, gz, m, c.ws, s, nullptr, &c);
+		tree_sort_points(c.treeM, gx, gy, gz, m, c.ws, s, &c);
 		c.mx.alloc(m);
 		c.my.alloc(m);
 		c.mz.alloc(m);

@@ -47,41 +47,25 @@ __global__ void k_bbox_finish(float *bbox)
 	if (threadIdx.x < 6) bbox[threadIdx.x] = float_unflip(((unsigned int *)bbox)[threadIdx.x]);
 }
 
-// Sort key (TREE_KEY_BITS = 48 bits).  Without `radius`: Hilbert index of the point's cell, 16 bits per axis
-// (cells of 1/65536 of the box, finer than the particle spacing in any realistic core; equal keys keep their
-// input order).  With `radius` (the ball radius of a scatterer): [47:42] = size class (half octaves of
-// extent/radius, largest balls first) and [41:0] = Hilbert index with 14 bits per axis, so that a bucket of 32
-// consecutive scatterers holds balls of similar size - the ball-inflated bucket box is then close to the balls
-// it holds and a point inside the box is likely inside the balls (tests per hit drop several-fold in clustered
-// data).
+// Sort key (TREE_KEY_BITS = 48 bits): Hilbert index of the point's cell, 16 bits per axis (cells of 1/65536 of the
+// box, finer than the particle spacing in any realistic core; equal keys keep their input order).
 __global__ void __launch_bounds__(256) k_sfc_keys(const float *x, const float *y, const float *z, int n,
-                                                  const float *bbox, const float *radius, uint64_t *keys,
-                                                  uint32_t *perm)
+                                                  const float *bbox, uint64_t *keys, uint32_t *perm)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	float p[3] = {x[i], y[i], z[i]};
 	uint32_t q[3];
-	double extMax = 0.0;
 #pragma unroll
 	for (int d = 0; d < 3; ++d) {
 		double ext = (double)bbox[3 + d] - (double)bbox[d];
-		if (ext > extMax) extMax = ext;
 		double t = ext > 0.0 ? ((double)p[d] - (double)bbox[d]) / ext : 0.0;
 		long long v = (long long)(t * 65536.0);
 		if (v < 0) v = 0;
 		if (v > 65535) v = 65535;
 		q[d] = (uint32_t)v;
 	}
-	uint64_t key;
-	if (radius) {
-		float h = radius[i];
-		int cls = 0;
-		if (h > 0.0f && extMax > 0.0) cls = (int)floorf(2.0f * log2f((float)extMax / h));
-		cls = cls < 0 ? 0 : (cls > 63 ? 63 : cls);
-		key = ((uint64_t)cls << 42) | hilbert3(q[0] >> 2, q[1] >> 2, q[2] >> 2, 14);
-	} else key = hilbert3(q[0], q[1], q[2], 16);
-	keys[i] = key;
+	keys[i] = hilbert3(q[0], q[1], q[2], 16);
 	perm[i] = (uint32_t)i;
 }
 
@@ -180,7 +164,7 @@ void dist_sort_pairs(skidgpu_ctx &c, uint64_t *keys, uint32_t *vals, size_t n, i
 }
 
 void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z, int n, Workspace &ws,
-                      cudaStream_t s, const float *radius, skidgpu_ctx *dist)
+                      cudaStream_t s, skidgpu_ctx *dist)
 {
 	t.n = n;
 	float *bbox = t.bbox.alloc(8);
@@ -188,7 +172,7 @@ void tree_sort_points(BoxTree &t, const float *x, const float *y, const float *z
 	uint32_t *perm = t.perm.alloc(n > 0 ? n : 1);
 	if (n == 0) return;
 	tree_bbox_only(t, x, y, z, n, s);
-	SK_LAUNCH(k_sfc_keys, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, radius, keys, perm);
+	SK_LAUNCH(k_sfc_keys, (unsigned)ceil_div(n, 256), 256, 0, s, x, y, z, n, bbox, keys, perm);
 	if (dist) dist_sort_pairs(*dist, keys, perm, n, TREE_KEY_BITS);
 	else radix_sort_pairs(keys, perm, n, TREE_KEY_BITS, ws, s);
 }
