@@ -1095,6 +1095,10 @@ static const uint32_t *wait_log(skidgpu_ctx &c, int b)
 	return c.hLog + 4 * (size_t)(b % LOG_SLOTS);
 }
 
+// (Measured and dropped, twice: running this kernel on a second stream - beside k_tile_step in round 1, beside
+// k_tile_filter for the tiles of overflowed supertiles in round 2 (queued by k_super_walk, so that the walks start
+// before the filter): list builds 73.5 -> 75.1 ms at 2^24, 49.2 -> 52.0 ms on the massive-halo box.  The kernels it
+// would hide behind are issue bound; what it gains in latency they lose in issue slots.)
 // k_tile_walk is latency bound (dependent tree loads): 8 resident blocks per SM (64 registers via the launch
 // bounds), persistent grid of that many blocks per SM, tiles drawn from a ticket counter.
 static void launch_tile_walk(skidgpu_ctx &c, const StepArgs &sa, const uint32_t *queue, const uint32_t *queueCount,
