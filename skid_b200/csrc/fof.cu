@@ -220,35 +220,40 @@ __global__ void __launch_bounds__(256) k_link_cells(const LinkArgs a)
 				if (B == A) B = -1;
 			}
 		}
-		uint32_t have = __ballot_sync(SK_FULL, B >= 0);
+		// The boxes of the two cells' movers decide most pairs of cells: converged clumps are much smaller than
+		// a cell, so two clumps farther apart than tau are rejected and two clumps well within tau are united
+		// without a mover-pair test.  (ncu on the version that always scanned the pairs: 11.3 ms at 2^24 for
+		// 4.7e8 warp instructions, 23 % warps active - a few warps scanning the nA x nB ~ 10^5 pairs of two
+		// unlinked dense cells, through a 64-bit division per pair, were the whole kernel.)  The bounds are a
+		// lower / upper bound of the min-image distance of any pair, with a 1e-5 margin on tau^2 for the
+		// float rounding of the exact test (coordinate differences this small are exact in float32).
+		// Every lane tests the box of the neighbour it found - 32 box fetches in flight instead of one after the
+		// other - and only the cells that can be linked are taken one by one below.
+		bool near = false, boxLinked = false;
+		if (B >= 0) {
+			const float4 blo = a.cellBox[2 * (size_t)B], bhi = a.cellBox[2 * (size_t)B + 1];
+			float gl2 = 0.0f, gh2 = 0.0f;
+			const float al[3] = {alo.x, alo.y, alo.z}, ah[3] = {ahi.x, ahi.y, ahi.z};
+			const float bl[3] = {blo.x, blo.y, blo.z}, bh[3] = {bhi.x, bhi.y, bhi.z};
+#pragma unroll
+			for (int d = 0; d < 3; ++d) {
+				const float direct = fmaxf(fmaxf(bl[d] - ah[d], al[d] - bh[d]), 0.0f);
+				const float span = fmaxf(ah[d], bh[d]) - fminf(al[d], bl[d]);
+				const float wrapped = fmaxf(a.L[d] - span, 0.0f); // the other way round the periodic axis
+				const float gmin = fminf(direct, wrapped);
+				const float sep = fmaxf(ah[d] - bl[d], bh[d] - al[d]);
+				gl2 = fmaf(gmin, gmin, gl2);
+				gh2 = fmaf(sep, sep, gh2);
+			}
+			near = gl2 <= a.fTau2 * 1.00001f;     // else: no mover of A is within tau of a mover of B
+			boxLinked = gh2 < a.fTau2 * 0.99999f; // every mover of A is within tau of every mover of B
+		}
+		uint32_t have = __ballot_sync(SK_FULL, near);
+		const uint32_t linkedByBox = __ballot_sync(SK_FULL, boxLinked);
 		while (have) {
 			int src = __ffs(have) - 1;
 			have &= have - 1;
 			int Bc = __shfl_sync(SK_FULL, B, src);
-			// The boxes of the two cells' movers decide most pairs of cells: converged clumps are much smaller than
-			// a cell, so two clumps farther apart than tau are rejected and two clumps well within tau are united
-			// without a mover-pair test.  (ncu on the version that always scanned the pairs: 11.3 ms at 2^24 for
-			// 4.7e8 warp instructions, 23 % warps active - a few warps scanning the nA x nB ~ 10^5 pairs of two
-			// unlinked dense cells, through a 64-bit division per pair, were the whole kernel.)  The bounds are a
-			// lower / upper bound of the min-image distance of any pair, with a 1e-5 margin on tau^2 for the
-			// float rounding of the exact test (coordinate differences this small are exact in float32).
-			const float4 blo = a.cellBox[2 * (size_t)Bc], bhi = a.cellBox[2 * (size_t)Bc + 1];
-			float gl2 = 0.0f, gh2 = 0.0f;
-			{
-				const float al[3] = {alo.x, alo.y, alo.z}, ah[3] = {ahi.x, ahi.y, ahi.z};
-				const float bl[3] = {blo.x, blo.y, blo.z}, bh[3] = {bhi.x, bhi.y, bhi.z};
-#pragma unroll
-				for (int d = 0; d < 3; ++d) {
-					const float direct = fmaxf(fmaxf(bl[d] - ah[d], al[d] - bh[d]), 0.0f);
-					const float span = fmaxf(ah[d], bh[d]) - fminf(al[d], bl[d]);
-					const float wrapped = fmaxf(a.L[d] - span, 0.0f); // the other way round the periodic axis
-					const float gmin = fminf(direct, wrapped);
-					const float sep = fmaxf(ah[d] - bl[d], bh[d] - al[d]);
-					gl2 = fmaf(gmin, gmin, gl2);
-					gh2 = fmaf(sep, sep, gh2);
-				}
-			}
-			if (gl2 > a.fTau2 * 1.00001f) continue; // no mover of A is within tau of a mover of B
 			// already in the same component?
 			uint32_t ra = 0, rb = 1;
 			if (lane == 0) {
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(256) k_link_cells(const LinkArgs a)
 			ra = __shfl_sync(SK_FULL, ra, 0);
 			rb = __shfl_sync(SK_FULL, rb, 0);
 			if (ra == rb) continue;
-			bool linked = gh2 < a.fTau2 * 0.99999f;     // every mover of A is within tau of every mover of B
+			bool linked = (linkedByBox >> src) & 1u;
 			if (!linked) {
 				const uint32_t bBeg = a.cellStart[Bc], bEnd = a.cellStart[Bc + 1];
 				const uint32_t nB = bEnd - bBeg;
