@@ -353,7 +353,7 @@ def main():
     if shard:
         # sharded vs single-GPU on the same small box, once, before the warm-up passes: the driver's evidence that
         # the N-rank run computes the single-GPU groups
-        from oracle.refdump import canonical_labels
+        canonical_labels = parallel.canonical_labels  # (the oracle is only touched by the CPU arms)
         ps = synth.make_box(1 << a.parity_log2n, seed=11, kind=a.kind)
         g_sh, cat_sh, unb_sh, before_sh = parallel.run_skid_sharded(sk, None, ps["pinit"], ps["nGas"], ps["nDark"], ps["nStar"],
                                                                     ps["flags"], rank, world, host=True, fetch=True)

@@ -74,6 +74,27 @@ def dist_sort_piece(keys, rank, nranks, samples=1 << 16):
     return idx[np.argsort(keys[idx], kind="stable")]
 
 
+def canonical_labels(grp):
+    """Relabel a partition so that groups are numbered by ascending smallest member index (0 stays 0): two
+    catalogues describe the same partition iff their canonical labels are equal (bench.py's sharded-vs-single
+    `parity`)."""
+    grp = np.asarray(grp)
+    out = np.zeros_like(grp)
+    idx = np.nonzero(grp)[0]
+    if len(idx) == 0:
+        return out
+    g = grp[idx]
+    big = np.iinfo(np.int64).max
+    first = np.full(int(g.max()) + 1, big, np.int64)
+    np.minimum.at(first, g, idx)
+    used = np.nonzero(first != big)[0]
+    order = used[np.argsort(first[used], kind="stable")]
+    remap = np.zeros(int(g.max()) + 1, np.int64)
+    remap[order] = np.arange(1, len(order) + 1)
+    out[idx] = remap[g]
+    return out
+
+
 def init_comm(sk, dist, rank, nranks):
     """Give the context its NCCL communicator: rank 0 makes the id, torch.distributed carries it."""
     from . import api
