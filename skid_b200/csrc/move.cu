@@ -209,6 +209,16 @@ enum { DT_T = 0, DT_MIN = 1, DT_QUEUE = 2, DT_TILEQ = 3, DT_SHORTQ = 5, DT_BIG =
        DT_STEPS = 12 /* 64-bit: mover-steps of this stage */, DT_WORDS = 16 };
 #define N_ACTIVE(a) ((int)(a).dT[DT_NACT + (a).par])
 
+// MUFU.RSQ of a float that is known to be normal (callers clamp to >= 1e-30): the plain rsqrtf() wraps the same
+// instruction in a denormal rescue (compare, two predicated multiplies) that never fires here - 3 of the 27
+// instructions of the spline term.  Same bits for normal inputs.
+__device__ __forceinline__ float rsqrt_normal(float v)
+{
+	float y;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v));
+	return y;
+}
+
 // kdMoveParticles (kd.c:711-729) for one mover.  The reference forms ai = fStep/sqrt(|a|^2) in double and
 // rounds it to float; here a refined float reciprocal square root gives the same value to <= 2 ulp
 // (a position change of ~1e-7 fStep, far below the float spacing of the coordinates), and the wrap
@@ -219,7 +229,7 @@ __device__ __forceinline__ void move_one(const StepArgs &a, uint32_t id, float x
 	const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
 	float ai;
 	if (s2 > 1.0e-30f && s2 < 1.0e30f) {
-		float yv = rsqrtf(s2);
+		float yv = rsqrt_normal(s2);
 		yv = yv * fmaf(-0.5f * s2, yv * yv, 1.5f); // one Newton step
 		ai = a.fStep * yv;
 	} else { // zero, denormal, huge or non-finite: the reference's own arithmetic
@@ -247,7 +257,7 @@ __device__ __forceinline__ void move_one(const StepArgs &a, uint32_t id, float x
 #define ACC_HIT(dx, dy, dz, d2, q)                                                                     \
 {                                                                                              \
 	const float r2_ = __fmul_rn((d2), (q).x);                                              \
-	float y_ = rsqrtf(fmaxf(r2_, 1.0e-30f));                                               \
+	float y_ = rsqrt_normal(fmaxf(r2_, 1.0e-30f));                                               \
 	float rs_ = r2_ * y_;                                                                  \
 	rs_ = fmaf(0.5f * y_, fmaf(-rs_, rs_, r2_), rs_);                                      \
 	y_ = fmaf(y_, fmaf(-rs_, y_, 1.0f), y_);                                               \
